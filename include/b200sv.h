@@ -1,0 +1,117 @@
+/*
+ * b200sv -- C ABI of the B200-native complex128 statevector engine.
+ *
+ * This is the drop-in boundary for blueqat's dense statevector path: every entry point below replaces a
+ * piece of blueqat/backends/numpy_backend.py (reference file:line given per function).  The host side
+ * (qaqarot_b200/backend.py, loaded through ctypes) keeps the reference's plugin interface
+ * (`Backend.run(gates, n_qubits, shots=, initial=, returns=, ...)`, backendbase.py:89-91) and calls down
+ * here for every pass over amplitudes.  No torch types, no C++ types: plain pointers and sizes.
+ *
+ * Conventions
+ *   - A state is 2^n complex128 amplitudes, interleaved (re, im), little endian in the qubit index:
+ *     bit k of the amplitude index is qubit k (numpy_backend.py:82-83).
+ *   - Every function returns 0 on success; otherwise b200_last_error() describes the failure
+ *     (thread local).  Functions are synchronous on return unless stated; one state must not be used
+ *     from two host threads at once.
+ *   - Host pointers are caller owned.  `b200_state*` handles are opaque and own their device memory
+ *     unless created with b200_state_wrap().
+ */
+#ifndef B200SV_H
+#define B200SV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_state b200_state;
+
+/* ---- op program ------------------------------------------------------------------------------- */
+
+enum {
+  B200_OP_MAT   = 1,  /* 2x2 on `target` where all `cmask` bits are 1: gate_x/y/h/rx/ry/u/mat1/cx/cu/crx/cry/ccx
+                         (numpy_backend.py:75-106,119-177,244-338,385-444).  reals: m00 m01 m10 m11 as (re,im) */
+  B200_OP_DIAG  = 2,  /* amp *= (bit(target) ? d1 : d0) where all `cmask` bits are 1: gate_z/s/t/phase/rz/cz/
+                         crz/cphase/ccz (:109-116,180-241,341-382).  reals: d0 d1 as (re,im)                */
+  B200_OP_X     = 3,  /* pair swap on `target` under `cmask` (x / cx / ccx as pure permutations)          */
+  B200_OP_SWAP  = 4,  /* exchange qubits `target` and `aux` (swap gate; reference falls back to 3 cx,
+                         gate.py:1172-1177)                                                                */
+  B200_OP_TILE  = 16, /* fused tile-resident pass: `woff/wlen` locate its descriptor in `words`            */
+  B200_OP_SCALE = 17  /* multiply the whole state by reals[0..1]                                           */
+};
+
+typedef struct b200_op {
+  int32_t  kind;    /* B200_OP_*                                            */
+  int32_t  target;  /* target qubit                                         */
+  int32_t  aux;     /* second qubit (SWAP)                                  */
+  int32_t  wlen;    /* TILE: descriptor length in 64-bit words              */
+  uint64_t cmask;   /* control mask over qubit indices (0 = uncontrolled)   */
+  uint64_t woff;    /* TILE: descriptor offset into `words`                 */
+  uint64_t roff;    /* offset of this op's payload in `reals` (doubles)     */
+} b200_op;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+
+const char* b200_last_error(void);
+int b200_device_count(int* out);
+int b200_version(void);
+
+/* ---- state lifetime (replaces _NumPyBackendContext.__init__/prepare, numpy_backend.py:36-62) ---- */
+
+int b200_state_create(int device, int n_qubits, b200_state** out);
+/* Adopt caller-owned device memory (e.g. a torch tensor's data_ptr) of 2^n_qubits complex128. */
+int b200_state_wrap(int device, int n_qubits, void* device_amps, b200_state** out);
+int b200_state_destroy(b200_state* st);
+int b200_state_n_qubits(const b200_state* st);
+void* b200_state_device_ptr(const b200_state* st);
+
+int b200_state_set_basis(b200_state* st, uint64_t index);                       /* prepare(): |index>      */
+int b200_state_upload(b200_state* st, const double* host, uint64_t offset, uint64_t count);   /* initial= */
+int b200_state_download(const b200_state* st, double* host, uint64_t offset, uint64_t count); /* returns   */
+int b200_state_copy(b200_state* dst, const b200_state* src);                    /* ctx.cache (:564-568)    */
+
+/* ---- unitary evolution (replaces _run_inner's gate loop, numpy_backend.py:545-570) -------------- */
+
+int b200_apply_program(b200_state* st, const b200_op* ops, int n_ops,
+                       const uint64_t* words, size_t n_words, const double* reals, size_t n_reals);
+/* Device time of the last b200_apply_program (CUDA events on the state's stream), in milliseconds. */
+int b200_last_program_ms(b200_state* st, double* ms);
+/* Per-op device times of the last program (only recorded while profiling is on). Returns count in *n. */
+int b200_set_profiling(b200_state* st, int on);
+int b200_last_op_times(b200_state* st, float* ms, int32_t* kinds, int cap, int* n);
+/* Number of kernels this library has launched on this state since creation. */
+int b200_launch_count(const b200_state* st, uint64_t* out);
+
+/* ---- measurement (replaces gate_measure / gate_reset, numpy_backend.py:447-497) ------------------ */
+
+int b200_prob_zero(b200_state* st, int target, double* p0);          /* ||psi[bit target = 0]||^2        */
+/* mode 0 = measure: keep `outcome` half, zero the other, scale by 1/sqrt(p).
+   mode 1 = reset  : as measure, then move the |1> half onto |0> when outcome = 1.                      */
+int b200_collapse(b200_state* st, int target, int outcome, double p, int mode);
+int b200_norm2(b200_state* st, double* out);
+int b200_scale(b200_state* st, double re, double im);
+/* First amplitude with |a| > eps in index order (utils.ignore_global_phase, utils.py:130-144).
+   *index = UINT64_MAX when there is none. */
+int b200_first_above(b200_state* st, double eps, uint64_t* index, double* re, double* im);
+
+/* Batched terminal-measurement sampler.  For each shot s, walks the measured qubits in `order`
+   (the reference's target_iter order), comparing uniforms[s*m + j] with the conditional probability
+   P(bit_j = 0 | earlier outcomes) exactly as repeated gate_measure calls would, without collapsing
+   the state.  out_bits[s] gets bit j set when qubit order[j] measured 1.  m <= 64.                     */
+int b200_sample(b200_state* st, const int32_t* order, int m, const double* uniforms, int n_shots,
+                uint64_t* out_bits);
+
+/* ---- Pauli expectation (replaces Expr.to_matrix + sparse_expectation, pauli.py:893-935,
+        vqe.py:355-366).  One group = all terms sharing the same X/Y flip mask `xmask`:
+        sum_i conj(psi[i ^ xmask]) * psi[i] * sum_k (cre_k + i cim_k) * (-1)^popcount(i & zymask_k).       */
+int b200_expect_group(b200_state* st, uint64_t xmask, int n_terms, const uint64_t* zymask,
+                      const double* cre, const double* cim, double* out_re, double* out_im);
+
+int b200_sync(b200_state* st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SV_H */

@@ -1,0 +1,180 @@
+"""numpy interpreter of the device op program.  TEST INFRASTRUCTURE -- never imported by the product.
+
+``OracleState`` has the method surface of ``qaqarot_b200.device.DeviceState`` and executes the *encoded*
+program arrays (struct b200_op[], words, reals -- exactly what crosses the C ABI) with numpy, so that the
+host-side logic (lowering, fusion planning, descriptor encoding, shot descent, cache handling) can be checked
+on a CPU against the reference fixtures, and so that GPU tests can compare the CUDA executor with an
+independent executor of the same program.  Tests inject it with ``B200Backend(state_factory=...)``.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence
+
+import numpy as np
+
+from oracle.sv_oracle import sub
+
+OP_MAT, OP_DIAG, OP_X, OP_SWAP, OP_TILE, OP_SCALE = 1, 2, 3, 4, 16, 17
+
+
+def _bits(mask: int):
+    return [b for b in range(mask.bit_length()) if mask >> b & 1]
+
+
+class OracleState:
+    def __init__(self, n_qubits: int, device: int = 0):
+        self.n_qubits = n_qubits
+        self.device = device
+        self.psi = np.zeros(1 << n_qubits, dtype=complex)
+        self.psi[0] = 1.0
+        self.launches = 0
+
+    # -- lifetime / contents --------------------------------------------------------------------
+    def close(self):
+        pass
+
+    @property
+    def dim(self):
+        return 1 << self.n_qubits
+
+    def set_basis(self, index=0):
+        self.psi[:] = 0.0
+        self.psi[index] = 1.0
+
+    def upload(self, vec, offset=0):
+        self.psi[offset:offset + vec.size] = vec
+
+    def download(self, offset=0, count=None, out=None):
+        count = self.dim - offset if count is None else count
+        res = self.psi[offset:offset + count].copy()
+        if out is not None:
+            out[:] = res
+            return out
+        return res
+
+    def copy_from(self, other):
+        self.psi[:] = other.psi
+
+    def clone(self):
+        c = OracleState(self.n_qubits)
+        c.psi[:] = self.psi
+        return c
+
+    # -- program execution ----------------------------------------------------------------------
+    def apply(self, program):
+        if len(program) == 0:
+            return
+        ops, n_ops, words, reals = program.frozen()
+        n = self.n_qubits
+        for i in range(n_ops):
+            o = ops[i]
+            ctrl = {c: 1 for c in _bits(o.cmask)}
+            if o.kind == OP_MAT:
+                m = reals[o.roff:o.roff + 8].view(complex)
+                q0 = sub(self.psi, n, {**ctrl, o.target: 0})
+                q1 = sub(self.psi, n, {**ctrl, o.target: 1})
+                n0 = m[0] * q0 + m[1] * q1
+                n1 = m[2] * q0 + m[3] * q1
+                q0[...] = n0
+                q1[...] = n1
+            elif o.kind == OP_X:
+                q0 = sub(self.psi, n, {**ctrl, o.target: 0})
+                q1 = sub(self.psi, n, {**ctrl, o.target: 1})
+                t = q0.copy()
+                q0[...] = q1
+                q1[...] = t
+            elif o.kind == OP_DIAG:
+                d = reals[o.roff:o.roff + 4].view(complex)
+                sub(self.psi, n, {**ctrl, o.target: 0})[...] *= d[0]
+                sub(self.psi, n, {**ctrl, o.target: 1})[...] *= d[1]
+            elif o.kind == OP_SWAP:
+                a = sub(self.psi, n, {o.target: 1, o.aux: 0})
+                b = sub(self.psi, n, {o.target: 0, o.aux: 1})
+                t = a.copy()
+                a[...] = b
+                b[...] = t
+            elif o.kind == OP_SCALE:
+                self.psi *= complex(reals[o.roff], reals[o.roff + 1])
+            elif o.kind == OP_TILE:
+                from oracle.tile_interp import run_tile_pass
+                run_tile_pass(self.psi, n, words[o.woff:o.woff + o.wlen], reals)
+            else:
+                raise ValueError(f"unknown op kind {o.kind}")
+            self.launches += 1
+
+    def last_program_ms(self):
+        return 0.0
+
+    def launch_count(self):
+        return self.launches
+
+    # -- measurement ----------------------------------------------------------------------------
+    def prob_zero(self, target):
+        v = sub(self.psi, self.n_qubits, {target: 0})
+        return float(np.sum(v.real ** 2 + v.imag ** 2))
+
+    def collapse(self, target, outcome, p, reset=False):
+        s = 1.0 / math.sqrt(p)
+        q0 = sub(self.psi, self.n_qubits, {target: 0})
+        q1 = sub(self.psi, self.n_qubits, {target: 1})
+        if outcome == 0:
+            q0[...] *= s
+            q1[...] = 0.0
+        elif reset:
+            q0[...] = q1 * s
+            q1[...] = 0.0
+        else:
+            q1[...] *= s
+            q0[...] = 0.0
+
+    def norm2(self):
+        return float(np.vdot(self.psi, self.psi).real)
+
+    def scale(self, z):
+        self.psi *= complex(z)
+
+    def first_above(self, eps):
+        hit = np.nonzero(np.abs(self.psi) > eps)[0]
+        if hit.size == 0:
+            return None
+        return int(hit[0]), complex(self.psi[hit[0]])
+
+    def sample(self, order: Sequence[int], uniforms: np.ndarray) -> np.ndarray:
+        """Same descent as csrc/sample.cu: conditional probabilities on the uncollapsed state."""
+        order = list(order)
+        uniforms = np.asarray(uniforms, dtype=float).reshape(-1, max(1, len(order)))
+        prob = self.psi.real ** 2 + self.psi.imag ** 2
+        out = np.zeros(uniforms.shape[0], dtype=np.uint64)
+        memo = {}
+        for s in range(uniforms.shape[0]):
+            fixed = {}
+            bits = 0
+            for j, q in enumerate(order):
+                if q in fixed:
+                    p0 = 0.0 if fixed[q] else 1.0
+                else:
+                    key = (tuple(sorted(fixed.items())), q)
+                    if key not in memo:
+                        s0 = float(np.sum(sub(prob, self.n_qubits, {**fixed, q: 0})))
+                        s1 = float(np.sum(sub(prob, self.n_qubits, {**fixed, q: 1})))
+                        memo[key] = s0 / (s0 + s1)
+                    p0 = memo[key]
+                bit = 0 if uniforms[s, j] < p0 else 1
+                fixed[q] = bit
+                bits |= bit << j
+            out[s] = bits
+        return out
+
+    def expect_group(self, xmask, zymasks, coeffs):
+        idx = np.arange(self.dim, dtype=np.int64)
+        w = np.zeros(self.dim, dtype=complex)
+        for zy, c in zip(zymasks, coeffs):
+            par = np.zeros(self.dim, dtype=np.int64)
+            for b in _bits(int(zy)):
+                par ^= (idx >> b) & 1
+            w += complex(c) * (1 - 2 * par)
+        return complex(np.sum(np.conj(self.psi[idx ^ int(xmask)]) * self.psi * w))
+
+    def sync(self):
+        pass

@@ -1,0 +1,417 @@
+"""``B200Backend`` -- the drop-in for blueqat's ``NumPyBackend`` on one B200.
+
+Same plugin interface and keyword arguments as the reference backend
+(``run(gates, n_qubits, shots=None, initial=None, returns=None, ignore_global=False, save_cache=False)``,
+blueqat/backends/numpy_backend.py:572-630; ``statevector / shots / oneshot / samples / make_cache``, :632-685;
+``copy``, backendbase.py:27-33), plus ``hamiltonian=`` following the convention of the reference's only
+consumer of that keyword (blueqat/backends/quimb.py:17-72: a float, taking precedence over shots).
+
+The host side only plans: operations are lowered to primitives (lowering.py), grouped into fused passes
+(planner.py) and handed to the CUDA library through the C ABI (device.py -> include/b200sv.h).  Randomness
+comes from Python's global ``random.random()`` in the reference's order -- one draw per measured / reset
+qubit per shot (numpy_backend.py:456, 488) -- so seeded runs reproduce NumPyBackend's Counters.
+
+There is no CPU path: constructing the first device state raises ``B200LibraryError`` / ``B200Error`` when
+the library or a GPU is missing.
+"""
+from __future__ import annotations
+
+import math
+import random
+import warnings
+from collections import Counter
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .lowering import Lowered, Prim, lower
+from .pauli import canonical_terms
+from .program import Program, unfused_program
+
+try:                                                   # subclass blueqat's base class when it is importable
+    from blueqat.backends.backendbase import Backend as _Base
+except Exception:                                      # blueqat absent (e.g. on the GPU box)
+    class _Base:                                       # minimal stand-in for backendbase.Backend
+        def copy(self):
+            raise NotImplementedError
+
+        def make_cache(self, gates, n_qubits):
+            return None
+
+DEFAULT_SHOTS = 1024                                   # numpy_backend.py:33
+RETURNS = ("statevector", "shots", "statevector_and_shots", "_inner_ctx", "samples")
+
+
+def _default_state_factory(n_qubits: int, device: int):
+    from .device import DeviceState
+    return DeviceState(n_qubits, device)
+
+
+class RunContext:
+    """What ``returns="_inner_ctx"`` hands back (backend-private in the reference, :521)."""
+
+    def __init__(self, n_qubits):
+        self.n_qubits = n_qubits
+        self.qubits: Optional[np.ndarray] = None
+        self.cregs: List[int] = [0] * n_qubits
+        self.shots_result: Counter = Counter()
+        self.samples: List[Dict[str, List[int]]] = []
+        self.device_state = None
+
+
+class _Compiled:
+    """Lowered + planned form of gates[start:], cached on the backend between runs of the same circuit."""
+
+    def __init__(self, gates: Sequence, n_qubits: int, start: int, planner: Callable[[Sequence[Prim], int], Program]):
+        self.gates = tuple(gates)
+        self.n_qubits = n_qubits
+        self.start = start
+        low = lower(self.gates[start:], n_qubits, start)
+        self.n_gates = low.n_gates
+        prims = low.prims
+        k = low.first_nonunitary if low.first_nonunitary is not None else len(prims)
+        self.prefix_prims = prims[:k]
+        self.prefix = planner(self.prefix_prims, n_qubits)
+        self.first_nonunitary_op = prims[k].op_index if k < len(prims) else None
+        # the rest: alternating unitary segments (as programs) and measure/reset primitives
+        self.rest: List[Any] = []
+        seg: List[Prim] = []
+        for p in prims[k:]:
+            if p.unitary:
+                seg.append(p)
+            else:
+                if seg:
+                    self.rest.append(planner(seg, n_qubits))
+                    seg = []
+                self.rest.append(p)
+        if seg:
+            self.rest.append(planner(seg, n_qubits))
+        self.terminal = bool(self.rest) and all(isinstance(r, Prim) and r.kind == "measure" for r in self.rest)
+
+    def matches(self, gates: Sequence, n_qubits: int, start: int) -> bool:
+        return (n_qubits == self.n_qubits and start == self.start and len(gates) == len(self.gates)
+                and all(a is b for a, b in zip(gates, self.gates)))
+
+
+def _check_initial(initial, n_qubits: int) -> np.ndarray:
+    """numpy_backend.py:500-512."""
+    if not isinstance(initial, np.ndarray):
+        raise ValueError(f"`initial` must be a np.ndarray, but {type(initial)}")
+    if initial.shape != (2 ** n_qubits,):
+        raise ValueError(f"`initial.shape` is not matched. Expected: {(2**n_qubits,)}, Actual: {initial.shape}")
+    if initial.dtype != complex:
+        initial = initial.astype(complex)
+    return initial
+
+
+class B200Backend(_Base):
+    """Statevector simulator backend running on one NVIDIA B200 through libb200sv.so."""
+
+    def __init__(self, device: int = 0, fusion: bool = True, state_factory=None, planner=None):
+        self.device = device
+        self.fusion = fusion
+        self.cache = None                    # device snapshot taken before the first Measurement/Reset
+        self.cache_idx = -1
+        self._state_factory = state_factory or _default_state_factory
+        if planner is None:
+            if fusion:
+                from .planner import plan as planner
+            else:
+                planner = lambda prims, n: unfused_program(prims)
+        self._planner = planner
+        self._work = None                    # reusable work state
+        self._compiled: Optional[_Compiled] = None
+        self.last_stats: Dict[str, Any] = {}
+
+    # -- Backend protocol -------------------------------------------------------------------------
+    def copy(self) -> "B200Backend":
+        """Device buffers cannot be deep-copied; clone the snapshot explicitly (backendbase.py:27-33)."""
+        other = B200Backend(self.device, self.fusion, self._state_factory, self._planner)
+        if self.cache is not None:
+            other.cache = self.cache.clone()
+            other.cache_idx = self.cache_idx
+        return other
+
+    def __deepcopy__(self, memo):
+        return self.copy()
+
+    def close(self) -> None:
+        for st in (self._work, self.cache):
+            if st is not None:
+                st.close()
+        self._work = self.cache = None
+        self.cache_idx = -1
+
+    def _clear_cache(self) -> None:
+        if self.cache is not None:
+            self.cache.close()
+        self.cache, self.cache_idx = None, -1
+
+    def _state(self, n_qubits: int):
+        if self._work is None or self._work.n_qubits != n_qubits:
+            if self._work is not None:
+                self._work.close()
+            self._work = self._state_factory(n_qubits, self.device)
+        return self._work
+
+    def _compile(self, gates: Sequence, n_qubits: int, start: int) -> _Compiled:
+        c = self._compiled
+        if c is None or not c.matches(gates, n_qubits, start):
+            c = self._compiled = _Compiled(gates, n_qubits, start, self._planner)
+        return c
+
+    # -- the run loop -----------------------------------------------------------------------------
+    def _execute(self, gates, n_qubits, shots: int, initial, save_cache: bool, want_final_state: bool,
+                 use_backend_cache: bool = True) -> RunContext:
+        """Counterpart of the shot loop + _run_inner (numpy_backend.py:545-570, 618-626)."""
+        ctx = RunContext(n_qubits)
+        cache, cache_idx = (self.cache, self.cache_idx) if use_backend_cache else (None, -1)
+        start = cache_idx + 1 if cache is not None else 0
+        comp = self._compile(gates, n_qubits, start)
+        st = self._state(n_qubits)
+        ctx.device_state = st
+        if cache is not None:
+            st.copy_from(cache)
+        elif initial is not None:
+            st.upload(initial)
+        else:
+            st.set_basis(0)
+        st.apply(comp.prefix)
+        self.last_stats = {"n_gates": comp.n_gates, "prefix_passes": comp.prefix.n_passes,
+                           "prefix_prims": comp.prefix.n_prims}
+        if not comp.rest:
+            # no measurement or reset: every shot leaves cregs = 0...0 (numpy_backend.py:622-623)
+            if n_qubits > 0:
+                ctx.shots_result["0" * n_qubits] = shots
+            ctx.samples = [{} for _ in range(shots)]
+            return ctx
+
+        snap = None
+        if shots > 1 or save_cache:
+            snap = st.clone()
+        if save_cache:
+            self._clear_cache()
+            self.cache, self.cache_idx = snap, comp.first_nonunitary_op - 1
+
+        if comp.terminal:
+            self._sample_terminal(ctx, comp, st, shots, want_final_state)
+        else:
+            for s in range(shots):
+                if s > 0:
+                    st.copy_from(snap)
+                self._trajectory(ctx, comp, st)
+        if snap is not None and not save_cache:
+            snap.close()
+        return ctx
+
+    def _trajectory(self, ctx: RunContext, comp: _Compiled, st) -> None:
+        """One shot through measure/reset one qubit at a time (gate_measure / gate_reset, :447-497)."""
+        cregs = [0] * ctx.n_qubits
+        sample: Dict[str, List[int]] = {}
+        pending: Optional[Tuple[Any, List[int]]] = None
+
+        def flush():
+            nonlocal pending
+            if pending is not None:
+                _store_key(sample, pending[0], pending[1])
+                pending = None
+
+        for item in comp.rest:
+            if isinstance(item, Program):
+                flush()
+                st.apply(item)
+                continue
+            if item.kind == "measure":
+                if pending is None or pending[0][2] != item.group[2]:
+                    flush()
+                    pending = (item.group, [])
+                if item.target < 0:
+                    continue
+            else:
+                flush()
+            p0 = st.prob_zero(item.target)
+            if random.random() < p0:
+                st.collapse(item.target, 0, p0, reset=item.kind == "reset")
+                bit = 0
+            else:
+                st.collapse(item.target, 1, 1.0 - p0, reset=item.kind == "reset")
+                bit = 1
+            if item.kind == "measure":
+                cregs[item.target] = bit
+                pending[1].append(bit)
+        flush()
+        ctx.cregs = cregs
+        ctx.samples.append(sample)
+        if cregs:
+            ctx.shots_result["".join(map(str, cregs))] += 1
+
+    def _sample_terminal(self, ctx: RunContext, comp: _Compiled, st, shots: int, want_final_state: bool) -> None:
+        """All shots of a circuit ending in measurements, in one batched descent (csrc/sample.cu)."""
+        meas = [p for p in comp.rest if p.target >= 0]
+        order = [p.target for p in meas]
+        m = len(order)
+        # the reference draws shot by shot, one uniform per measured qubit in target_iter order
+        uniforms = np.array([random.random() for _ in range(shots * m)], dtype=np.float64).reshape(shots, max(m, 1))
+        bits_all = np.zeros(shots, dtype=object)
+        for lo in range(0, m, 64):                      # the device call takes <= 64 qubits at a time
+            hi = min(m, lo + 64)
+            if lo == 0:
+                chunk = st.sample(order[lo:hi], uniforms[:, lo:hi])
+                for s in range(shots):
+                    bits_all[s] = int(chunk[s])
+            else:                                       # pragma: no cover - needs > 64 measured qubits
+                raise ValueError("more than 64 measured qubits in a terminal measurement are not supported")
+        n = ctx.n_qubits
+        for s in range(shots):
+            b = bits_all[s]
+            cregs = [0] * n
+            sample: Dict[str, List[int]] = {}
+            j = 0
+            groups: List[Tuple[Any, List[int]]] = []
+            for p in comp.rest:
+                if not groups or groups[-1][0][2] != p.group[2]:
+                    groups.append((p.group, []))
+                if p.target < 0:
+                    continue
+                bit = (b >> j) & 1
+                j += 1
+                cregs[p.target] = bit
+                groups[-1][1].append(bit)
+            for grp, vals in groups:
+                _store_key(sample, grp, vals)
+            ctx.samples.append(sample)
+            ctx.shots_result["".join(map(str, cregs))] += 1
+            ctx.cregs = cregs
+        if want_final_state and shots > 0:
+            b = bits_all[shots - 1]
+            for j, q in enumerate(order):
+                bit = (b >> j) & 1
+                p0 = st.prob_zero(q)
+                st.collapse(q, bit, (1.0 - p0) if bit else p0)
+
+    # -- public entry points ----------------------------------------------------------------------
+    def run(self, gates, n_qubits, shots: Optional[int] = None, initial: Optional[np.ndarray] = None,
+            returns: Optional[str] = None, ignore_global: bool = False, save_cache: bool = False,
+            hamiltonian=None, **kwargs) -> Any:
+        if hamiltonian is not None:
+            if kwargs:
+                warnings.warn(f"Unknown run arguments: {kwargs}")
+            return self.expectation(gates, n_qubits, hamiltonian, initial=initial)
+        if returns is None:
+            returns = "statevector" if shots is None else "shots"
+        if returns not in RETURNS:
+            raise ValueError(f"Unknown returns type '{returns}'")
+        if shots is None:
+            shots = 1 if returns in ("statevector", "_inner_ctx") else DEFAULT_SHOTS
+        if returns == "statevector" and shots > 1:
+            shots = 1
+            warnings.warn("When `returns` = 'statevector', `shots` is ignored.")
+        if kwargs:
+            warnings.warn(f"Unknown run arguments: {kwargs}")
+        if returns == "samples":
+            return self.samples(gates, n_qubits, shots, initial)
+
+        if initial is not None:
+            initial = _check_initial(initial, n_qubits)
+            if save_cache:
+                warnings.warn("When initial is not None, saving cache is disabled.")
+                save_cache = False
+            self._clear_cache()
+        elif self.cache is not None and self.cache.n_qubits != n_qubits:
+            self._clear_cache()
+
+        want_state = returns != "shots"
+        ctx = self._execute(gates, n_qubits, shots, initial, save_cache, want_state)
+        if returns == "shots":
+            return ctx.shots_result
+        st = ctx.device_state
+        if ignore_global:
+            _ignore_global_phase(st)
+        ctx.qubits = st.download()
+        if returns == "statevector":
+            return ctx.qubits
+        if returns == "statevector_and_shots":
+            return ctx.qubits, ctx.shots_result
+        return ctx
+
+    def statevector(self, gates, n_qubits, initial: Optional[np.ndarray] = None) -> np.ndarray:
+        if initial is not None:
+            initial = _check_initial(initial, n_qubits)
+        ctx = self._execute(gates, n_qubits, 1, initial, False, True, use_backend_cache=False)
+        return ctx.device_state.download()
+
+    def shots(self, gates, n_qubits, shots: int, initial: Optional[np.ndarray] = None):
+        if initial is not None:
+            initial = _check_initial(initial, n_qubits)
+        return self._execute(gates, n_qubits, shots, initial, False, False, use_backend_cache=False).shots_result
+
+    def oneshot(self, gates, n_qubits, initial: Optional[np.ndarray] = None):
+        if initial is not None:
+            initial = _check_initial(initial, n_qubits)
+        ctx = self._execute(gates, n_qubits, 1, initial, False, True, use_backend_cache=False)
+        return ctx.device_state.download(), ctx.shots_result.most_common()[0][0]
+
+    def samples(self, gates, n_qubits, shots: int, initial: Optional[np.ndarray] = None):
+        """Experimental in the reference (numpy_backend.py:669-682)."""
+        if initial is not None:
+            initial = _check_initial(initial, n_qubits)
+        return self._execute(gates, n_qubits, shots, initial, False, False, use_backend_cache=False).samples
+
+    def make_cache(self, gates, n_qubits) -> None:
+        self.run(gates, n_qubits, save_cache=True)
+
+    def expectation(self, gates, n_qubits, hamiltonian, initial: Optional[np.ndarray] = None) -> float:
+        """<psi| H |psi> for a Pauli expression, evaluated on the device without copying the state."""
+        terms = canonical_terms(hamiltonian)
+        for _, letters in terms:
+            for _, q in letters:
+                if not 0 <= q < n_qubits:
+                    raise ValueError(f"hamiltonian acts on qubit {q}, circuit has {n_qubits} qubits")
+        if initial is not None:
+            initial = _check_initial(initial, n_qubits)
+        ctx = self._execute(gates, n_qubits, 1, initial, False, True, use_backend_cache=initial is None)
+        return expectation_on_state(ctx.device_state, terms)
+
+
+def expectation_on_state(st, terms) -> float:
+    groups: Dict[int, Tuple[List[int], List[complex]]] = {}
+    for coeff, letters in terms:
+        xmask = zy = ny = 0
+        for letter, q in letters:
+            if letter in "XY":
+                xmask |= 1 << q
+            if letter in "YZ":
+                zy |= 1 << q
+            ny += letter == "Y"
+        g = groups.setdefault(xmask, ([], []))
+        g[0].append(zy)
+        g[1].append(complex(coeff) * (1j) ** ny)
+    total = 0.0 + 0.0j
+    for xmask in sorted(groups):
+        zys, coeffs = groups[xmask]
+        total += st.expect_group(xmask, zys, coeffs)
+    return float(total.real)
+
+
+def _store_key(sample: Dict[str, List[int]], group, measured: List[int]) -> None:
+    """Measurement-key bookkeeping of gate_measure (numpy_backend.py:467-476)."""
+    key, duplicated, _ = group
+    if key is None:
+        return
+    if key in sample:
+        if duplicated == "replace":
+            sample[key] = measured
+        elif duplicated == "append":
+            sample[key] = sample[key] + measured
+        else:
+            raise ValueError("Measurement key is duplicated.")
+    else:
+        sample[key] = measured
+
+
+def _ignore_global_phase(st) -> None:
+    """utils.ignore_global_phase (utils.py:130-144) on the device-resident state."""
+    hit = st.first_above(0.0000001)
+    if hit is not None:
+        q = hit[1]
+        st.scale(abs(q) / q)

@@ -1,0 +1,175 @@
+// sample.cu -- batched terminal-measurement sampler (sm_100a).
+//
+// Replaces the reference's shot loop for circuits that end in measurements: numpy re-executes
+// gate_measure per shot and per measured qubit (numpy_backend.py:447-477, 620-623), each a full pass with a
+// collapse.  Here all shots descend the measurement tree together, one level per measured qubit in the
+// reference's target_iter order.  At level j the shots that share the same earlier outcomes form a group;
+// one kernel computes, for every group, S0 = ||psi[group, q_j = 0]||^2 and S1 = ||psi[group, q_j = 1]||^2 over
+// the *uncollapsed* state, and the host compares the shot's own uniform with p0 = S0 / (S0 + S1), exactly the
+// comparison `rand < p_zero` the reference makes on its renormalised state.  The work per level is
+// min(2^j, shots) * 2^(n-j) amplitudes, so the whole descent costs about log2(shots) + 2 passes, independent
+// of the number of shots.  Sums are two-stage and fixed-order, hence run-to-run deterministic.
+#include "common.cuh"
+
+#include <algorithm>
+#include <numeric>
+
+namespace b200 {
+
+struct FreeRuns {          // maximal runs of free (not yet fixed, not current) index bits, ascending
+  int n;
+  unsigned char start[40];
+  unsigned char len[40];
+};
+
+__device__ __forceinline__ uint64_t deposit(uint64_t k, const FreeRuns& fr) {
+  uint64_t i = 0;
+  for (int r = 0; r < fr.n; ++r) {
+    const int len = fr.len[r];
+    i |= (k & ((1ull << len) - 1ull)) << fr.start[r];
+    k >>= len;
+  }
+  return i;
+}
+
+constexpr int kSampThreads = 256;
+
+__global__ void __launch_bounds__(kSampThreads)
+k_cond_prob(const c128* __restrict__ amp, uint64_t count, FreeRuns fr, const uint64_t* __restrict__ group_bits,
+            uint64_t tbit, int bx, double* __restrict__ partial) {
+  const int g = blockIdx.x / bx, b = blockIdx.x % bx;
+  const uint64_t fixed = group_bits[g];
+  double s0 = 0.0, s1 = 0.0;
+  const uint64_t stride = (uint64_t)bx * blockDim.x;
+  for (uint64_t k = (uint64_t)b * blockDim.x + threadIdx.x; k < count; k += stride) {
+    const uint64_t i = deposit(k, fr) | fixed;
+    const c128 a0 = amp[i], a1 = amp[i | tbit];
+    s0 += a0.x * a0.x + a0.y * a0.y;
+    s1 += a1.x * a1.x + a1.y * a1.y;
+  }
+  __shared__ double sh0[kSampThreads / 32], sh1[kSampThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sh0[w] = s0; sh1[w] = s1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int i = 0; i < kSampThreads / 32; ++i) { t0 += sh0[i]; t1 += sh1[i]; }
+    partial[2 * (size_t)blockIdx.x] = t0;
+    partial[2 * (size_t)blockIdx.x + 1] = t1;
+  }
+}
+
+__global__ void k_group_finish(const double* __restrict__ partial, int n_groups, int bx, double* __restrict__ out) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  double t0 = 0.0, t1 = 0.0;
+  for (int b = 0; b < bx; ++b) {
+    t0 += partial[2 * ((size_t)g * bx + b)];
+    t1 += partial[2 * ((size_t)g * bx + b) + 1];
+  }
+  out[2 * (size_t)g] = t0;
+  out[2 * (size_t)g + 1] = t1;
+}
+
+struct DeviceBuf {
+  void* p = nullptr;
+  ~DeviceBuf() { if (p) cudaFree(p); }
+};
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_sample(b200_state* st, const int32_t* order, int m, const double* uniforms, int n_shots,
+                           uint64_t* out_bits) {
+  B200_REQUIRE(st != nullptr && out_bits != nullptr, "b200_sample: null argument");
+  B200_REQUIRE(m >= 0 && m <= 64, "b200_sample: at most 64 measured qubits per call");
+  B200_REQUIRE(n_shots >= 0, "b200_sample: negative shot count");
+  B200_REQUIRE(m == 0 || (order != nullptr && uniforms != nullptr), "b200_sample: null order/uniforms");
+  for (int j = 0; j < m; ++j) B200_REQUIRE(order[j] >= 0 && order[j] < st->n, "b200_sample: qubit out of range");
+  std::fill(out_bits, out_bits + n_shots, 0ull);
+  if (m == 0 || n_shots == 0) return 0;
+  B200_CUDA(cudaSetDevice(st->device));
+
+  const int max_blocks = kSMs * 16;
+  const size_t max_groups = (size_t)n_shots;
+  DeviceBuf d_bits, d_partial, d_out;
+  B200_CUDA(cudaMalloc(&d_bits.p, sizeof(uint64_t) * max_groups));
+  B200_CUDA(cudaMalloc(&d_partial.p, sizeof(double) * 2 * (max_groups + (size_t)max_blocks)));
+  B200_CUDA(cudaMalloc(&d_out.p, sizeof(double) * 2 * max_groups));
+
+  std::vector<uint64_t> prefix(n_shots, 0ull);        // outcomes so far, as index bits
+  std::vector<int> idx(n_shots), group_of(n_shots);
+  std::vector<uint64_t> group_bits;
+  std::vector<double> sums;
+  uint64_t fixed_mask = 0;
+
+  for (int j = 0; j < m; ++j) {
+    const int q = order[j];
+    const uint64_t tbit = 1ull << q;
+    if (fixed_mask & tbit) {
+      // measured before: the state is already collapsed on this qubit, p_zero is 1 or 0.
+      for (int s = 0; s < n_shots; ++s) {
+        const double p0 = (prefix[s] & tbit) ? 0.0 : 1.0;
+        if (!(uniforms[(size_t)s * m + j] < p0)) out_bits[s] |= 1ull << j;
+      }
+      continue;
+    }
+    // group the shots by their outcomes so far
+    std::iota(idx.begin(), idx.end(), 0);
+    std::sort(idx.begin(), idx.end(), [&](int a, int b) { return prefix[a] < prefix[b]; });
+    group_bits.clear();
+    for (int r = 0; r < n_shots; ++r) {
+      const int s = idx[r];
+      if (r == 0 || prefix[s] != group_bits.back()) group_bits.push_back(prefix[s]);
+      group_of[s] = (int)group_bits.size() - 1;
+    }
+    const int n_groups = (int)group_bits.size();
+    // free bits = everything not fixed and not the current qubit
+    FreeRuns fr;
+    fr.n = 0;
+    int free_bits = 0;
+    for (int b = 0; b < st->n;) {
+      if ((fixed_mask | tbit) >> b & 1) { ++b; continue; }
+      int e = b;
+      while (e < st->n && !((fixed_mask | tbit) >> e & 1)) ++e;
+      fr.start[fr.n] = (unsigned char)b;
+      fr.len[fr.n] = (unsigned char)(e - b);
+      ++fr.n;
+      free_bits += e - b;
+      b = e;
+    }
+    const uint64_t count = 1ull << free_bits;
+    uint64_t want = (count + (uint64_t)kSampThreads * 4 - 1) / ((uint64_t)kSampThreads * 4);
+    int bx = (int)std::min<uint64_t>(want, (uint64_t)std::max(1, max_blocks / n_groups));
+    if (bx < 1) bx = 1;
+    B200_CUDA(cudaMemcpyAsync(d_bits.p, group_bits.data(), sizeof(uint64_t) * n_groups, cudaMemcpyHostToDevice,
+                              st->stream));
+    k_cond_prob<<<n_groups * bx, kSampThreads, 0, st->stream>>>(st->amp, count, fr, (const uint64_t*)d_bits.p, tbit, bx,
+                                                               (double*)d_partial.p);
+    B200_CUDA(cudaGetLastError());
+    k_group_finish<<<(n_groups + 127) / 128, 128, 0, st->stream>>>((const double*)d_partial.p, n_groups, bx,
+                                                                   (double*)d_out.p);
+    B200_CUDA(cudaGetLastError());
+    st->launches += 2;
+    sums.resize(2 * (size_t)n_groups);
+    B200_CUDA(cudaMemcpyAsync(sums.data(), d_out.p, sizeof(double) * 2 * n_groups, cudaMemcpyDeviceToHost, st->stream));
+    B200_CUDA(cudaStreamSynchronize(st->stream));
+    for (int s = 0; s < n_shots; ++s) {
+      const int g = group_of[s];
+      const double s0 = sums[2 * (size_t)g], s1 = sums[2 * (size_t)g + 1];
+      const double p0 = s0 / (s0 + s1);
+      if (!(uniforms[(size_t)s * m + j] < p0)) {
+        out_bits[s] |= 1ull << j;
+        prefix[s] |= tbit;
+      }
+    }
+    fixed_mask |= tbit;
+  }
+  return 0;
+}

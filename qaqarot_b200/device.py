@@ -1,0 +1,149 @@
+"""DeviceState: a 2^n complex128 statevector resident in B200 HBM, driven through the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .program import Program
+
+
+class DeviceState:
+    """Owns (or wraps) one device buffer.  All methods are synchronous; errors raise ``B200Error``."""
+
+    def __init__(self, n_qubits: int, device: int = 0, wrap_ptr: Optional[int] = None):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self.n_qubits = n_qubits
+        self.device = device
+        if wrap_ptr is None:
+            _lib.check(self._lib.b200_state_create(device, n_qubits, C.byref(self._h)))
+        else:
+            _lib.check(self._lib.b200_state_wrap(device, n_qubits, C.c_void_p(wrap_ptr), C.byref(self._h)))
+
+    # -- lifetime ---------------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.b200_state_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def dim(self) -> int:
+        return 1 << self.n_qubits
+
+    @property
+    def device_ptr(self) -> int:
+        return self._lib.b200_state_device_ptr(self._h) or 0
+
+    # -- contents ---------------------------------------------------------------------------------
+    def set_basis(self, index: int = 0) -> None:
+        _lib.check(self._lib.b200_state_set_basis(self._h, index))
+
+    def upload(self, vec: np.ndarray, offset: int = 0) -> None:
+        vec = np.ascontiguousarray(vec, dtype=np.complex128)
+        _lib.check(self._lib.b200_state_upload(self._h, vec.ctypes.data_as(C.c_void_p), offset, vec.size))
+
+    def download(self, offset: int = 0, count: Optional[int] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
+        count = self.dim - offset if count is None else count
+        if out is None:
+            out = np.empty(count, dtype=np.complex128)
+        assert out.dtype == np.complex128 and out.size == count and out.flags.c_contiguous
+        _lib.check(self._lib.b200_state_download(self._h, out.ctypes.data_as(C.c_void_p), offset, count))
+        return out
+
+    def copy_from(self, other: "DeviceState") -> None:
+        _lib.check(self._lib.b200_state_copy(self._h, other._h))
+
+    def clone(self) -> "DeviceState":
+        c = DeviceState(self.n_qubits, self.device)
+        c.copy_from(self)
+        return c
+
+    # -- evolution --------------------------------------------------------------------------------
+    def apply(self, program: Program) -> None:
+        if len(program) == 0:
+            return
+        ops, n_ops, words, reals = program.frozen()
+        _lib.check(self._lib.b200_apply_program(
+            self._h, ops, n_ops, words.ctypes.data_as(C.c_void_p), words.size,
+            reals.ctypes.data_as(C.c_void_p), reals.size))
+
+    def last_program_ms(self) -> float:
+        ms = C.c_double()
+        _lib.check(self._lib.b200_last_program_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def set_profiling(self, on: bool) -> None:
+        _lib.check(self._lib.b200_set_profiling(self._h, int(on)))
+
+    def last_op_times(self) -> Tuple[np.ndarray, np.ndarray]:
+        n = C.c_int()
+        _lib.check(self._lib.b200_last_op_times(self._h, None, None, 0, C.byref(n)))
+        ms = np.zeros(n.value, dtype=np.float32)
+        kinds = np.zeros(n.value, dtype=np.int32)
+        if n.value:
+            _lib.check(self._lib.b200_last_op_times(self._h, ms.ctypes.data_as(C.c_void_p),
+                                                    kinds.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
+        return ms, kinds
+
+    def launch_count(self) -> int:
+        v = C.c_uint64()
+        _lib.check(self._lib.b200_launch_count(self._h, C.byref(v)))
+        return v.value
+
+    # -- measurement ------------------------------------------------------------------------------
+    def prob_zero(self, target: int) -> float:
+        p = C.c_double()
+        _lib.check(self._lib.b200_prob_zero(self._h, target, C.byref(p)))
+        return p.value
+
+    def collapse(self, target: int, outcome: int, p: float, reset: bool = False) -> None:
+        _lib.check(self._lib.b200_collapse(self._h, target, outcome, p, int(reset)))
+
+    def norm2(self) -> float:
+        p = C.c_double()
+        _lib.check(self._lib.b200_norm2(self._h, C.byref(p)))
+        return p.value
+
+    def scale(self, z: complex) -> None:
+        z = complex(z)
+        _lib.check(self._lib.b200_scale(self._h, z.real, z.imag))
+
+    def first_above(self, eps: float) -> Optional[Tuple[int, complex]]:
+        idx, re, im = C.c_uint64(), C.c_double(), C.c_double()
+        _lib.check(self._lib.b200_first_above(self._h, eps, C.byref(idx), C.byref(re), C.byref(im)))
+        if idx.value == 0xFFFFFFFFFFFFFFFF:
+            return None
+        return idx.value, complex(re.value, im.value)
+
+    def sample(self, order: Sequence[int], uniforms: np.ndarray) -> np.ndarray:
+        """uniforms: (n_shots, m) float64 -> (n_shots,) uint64, bit j set when qubit order[j] read 1."""
+        order = np.ascontiguousarray(order, dtype=np.int32)
+        uniforms = np.ascontiguousarray(uniforms, dtype=np.float64).reshape(-1, max(1, order.size))
+        n_shots = uniforms.shape[0]
+        out = np.zeros(n_shots, dtype=np.uint64)
+        _lib.check(self._lib.b200_sample(self._h, order.ctypes.data_as(C.c_void_p), order.size,
+                                         uniforms.ctypes.data_as(C.c_void_p), n_shots,
+                                         out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def expect_group(self, xmask: int, zymasks: Sequence[int], coeffs: Sequence[complex]) -> complex:
+        zy = np.ascontiguousarray(zymasks, dtype=np.uint64)
+        cre = np.ascontiguousarray([complex(c).real for c in coeffs], dtype=np.float64)
+        cim = np.ascontiguousarray([complex(c).imag for c in coeffs], dtype=np.float64)
+        re, im = C.c_double(), C.c_double()
+        _lib.check(self._lib.b200_expect_group(self._h, xmask, zy.size, zy.ctypes.data_as(C.c_void_p),
+                                               cre.ctypes.data_as(C.c_void_p), cim.ctypes.data_as(C.c_void_p),
+                                               C.byref(re), C.byref(im)))
+        return complex(re.value, im.value)
+
+    def sync(self) -> None:
+        _lib.check(self._lib.b200_sync(self._h))

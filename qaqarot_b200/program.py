@@ -1,0 +1,80 @@
+"""Device op program: the arrays handed to ``b200_apply_program`` (include/b200sv.h)."""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import numpy as np
+
+from . import _lib
+from .lowering import Prim
+
+
+class Program:
+    """ops (struct b200_op[]), words (uint64 descriptor pool), reals (float64 payload pool)."""
+
+    def __init__(self):
+        self._ops: List[tuple] = []
+        self._words: List[int] = []
+        self._reals: List[float] = []
+        self.n_prims = 0          # primitives folded into this program
+        self.n_passes = 0         # state passes (one per op)
+        self.pass_bytes = 0.0     # algorithmic bytes moved, summed over passes (set by the planner)
+        self._frozen = None
+
+    # -- building -------------------------------------------------------------------------------
+    def add_reals(self, values: Sequence[complex]) -> int:
+        off = len(self._reals)
+        for v in values:
+            v = complex(v)
+            self._reals += [v.real, v.imag]
+        return off
+
+    def add_words(self, values: Sequence[int]) -> int:
+        off = len(self._words)
+        self._words += [int(v) & 0xFFFFFFFFFFFFFFFF for v in values]
+        return off
+
+    def add_op(self, kind: int, target: int = 0, aux: int = 0, cmask: int = 0, roff: int = 0, woff: int = 0,
+               wlen: int = 0) -> None:
+        self._ops.append((kind, target, aux, wlen, cmask, woff, roff))
+        self.n_passes += 1
+        self._frozen = None
+
+    def add_prim(self, p: Prim) -> None:
+        """One primitive as its own single-gate pass."""
+        cmask = 0
+        for c in p.controls:
+            cmask |= 1 << c
+        if p.kind == "mat":
+            self.add_op(_lib.OP_MAT, p.target, cmask=cmask, roff=self.add_reals(p.data))
+        elif p.kind == "diag":
+            self.add_op(_lib.OP_DIAG, p.target, cmask=cmask, roff=self.add_reals(p.data))
+        elif p.kind == "x":
+            self.add_op(_lib.OP_X, p.target, cmask=cmask)
+        elif p.kind == "swap":
+            self.add_op(_lib.OP_SWAP, p.target, aux=p.aux)
+        else:
+            raise ValueError(f"primitive {p.kind} is not a unitary pass")
+        self.n_prims += 1
+
+    # -- consumption ----------------------------------------------------------------------------
+    def frozen(self):
+        if self._frozen is None:
+            ops = (_lib.Op * max(1, len(self._ops)))()
+            for i, (kind, target, aux, wlen, cmask, woff, roff) in enumerate(self._ops):
+                o = ops[i]
+                o.kind, o.target, o.aux, o.wlen, o.cmask, o.woff, o.roff = kind, target, aux, wlen, cmask, woff, roff
+            words = np.asarray(self._words, dtype=np.uint64)
+            reals = np.asarray(self._reals, dtype=np.float64)
+            self._frozen = (ops, len(self._ops), words, reals)
+        return self._frozen
+
+    def __len__(self):
+        return len(self._ops)
+
+
+def unfused_program(prims: Sequence[Prim]) -> Program:
+    prog = Program()
+    for p in prims:
+        prog.add_prim(p)
+    return prog

@@ -1,0 +1,174 @@
+"""Parity of the CUDA path (through the C ABI) against the reference fixtures and the CPU oracle.
+
+Run on the B200 box: ``python -m pytest tests -m gpu``.  Tolerance: 1e-12 max-abs on amplitudes
+(BASELINE.json north_star); shot Counters must be equal for the same seeded ``random.random()`` stream.
+"""
+import random
+import warnings
+from collections import Counter
+
+import numpy as np
+import pytest
+
+import cases as C
+from conftest import case_names
+from helpers import TOL, maxabs, run_case
+from oracle import sv_oracle as O
+from qaqarot_b200 import B200Backend, Circuit, X, Y, Z
+
+pytestmark = pytest.mark.gpu
+MODES = [False, True]
+
+
+@pytest.fixture(scope="module", params=MODES, ids=["unfused", "fused"])
+def backend(request):
+    be = B200Backend(fusion=request.param)
+    yield be
+    be.close()
+
+
+@pytest.mark.parametrize("name", case_names("statevector"))
+def test_statevector_cases(name, backend, gold):
+    assert maxabs(run_case(gold.cases[name], backend), gold.sv(name)) <= TOL
+
+
+@pytest.mark.parametrize("name", case_names("shots"))
+def test_shot_cases(name, backend, gold):
+    assert dict(run_case(gold.cases[name], backend)) == gold.meta["cases"][name]["shots"]
+
+
+def test_statevector_and_shots(backend, gold):
+    sv, cnt = run_case(gold.cases["sv_and_shots"], backend)
+    assert dict(cnt) == gold.meta["cases"]["sv_and_shots"]["shots"]
+    assert maxabs(sv, gold.sv("sv_and_shots")) <= TOL
+
+
+def test_samples(backend, gold):
+    assert run_case(gold.cases["samples_keys"], backend) == gold.meta["cases"]["samples_keys"]["samples"]
+
+
+def test_hamiltonian(backend, gold):
+    letter = {"X": X, "Y": Y, "Z": Z}
+    for name, recs in gold.meta["expect"].items():
+        for rec in recs:
+            h = 0
+            for coeff, letters in rec["terms"]:
+                t = coeff
+                for ch, q in letters:
+                    t = t * letter[ch][q]
+                h = h + t
+            circ = C.build(Circuit, gold.cases[name])
+            init = C.initial_state(gold.cases[name])
+            kw = {} if init is None else {"initial": init}
+            assert abs(circ.run(backend=backend, hamiltonian=h, **kw) - rec["value"]) < 1e-10
+
+
+def _oracle(circ, **kw):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return O.OracleBackend().run(circ.ops, circ.n_qubits, **kw)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 11, 14, 17, 20])
+def test_every_target_position_against_oracle(n, backend):
+    """Each single-gate kernel on every qubit position (low strides through high strides)."""
+    rng = np.random.default_rng(n)
+    init = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
+    init /= np.linalg.norm(init)
+    c = Circuit(n)
+    for t in range(n):
+        c.h[t].rx(0.3 + t)[t].t[t].rz(0.1 * t + 0.2)[t].u(0.4, 0.5 + t, 0.6, 0.7)[t].x[t].y[t]
+        if n > 1:
+            o = (t + 1 + int(rng.integers(n - 1))) % n
+            c.cx[o, t].cz[t, o].cu(0.3, 0.2, 0.1, 0.5)[o, t].crz(0.9)[t, o].cphase(0.7)[o, t].swap[o, t]
+        if n > 2:
+            a, b = [q for q in rng.permutation(n) if q != t][:2]
+            c.ccx[int(a), int(b), t].ccz[t, int(a), int(b)]
+    assert maxabs(c.run(backend=backend, initial=init), _oracle(c, initial=init)) <= TOL
+
+
+@pytest.mark.parametrize("n,depth", [(16, 20), (20, 20)])
+def test_c1_random_layers(n, depth, backend):
+    """BASELINE configs[0]: Circuit(20) random H/RZ/CX layers depth 20, statevector + shots=1000."""
+    case = {"name": "c1", "n": n, "ops": C.random_layer_ops(n, depth), "initial_seed": None,
+            "run": {"shots": None, "seed": None, "returns": None}}
+    circ = C.build(Circuit, case)
+    ref = _oracle(circ)
+    assert maxabs(circ.run(backend=backend), ref) <= TOL
+    circ.m[:]
+    shots = 1000 if n <= 16 else 200
+    random.seed(7)
+    want = _oracle(circ, shots=shots)
+    random.seed(7)
+    assert circ.run(backend=backend, shots=shots) == want
+
+
+@pytest.mark.parametrize("n", [12, 18, 21])
+def test_c2_qft(n, backend):
+    """BASELINE configs[1] at oracle-sized n: against the oracle and the analytic answer."""
+    x = 123456789 % (1 << n)
+    case = {"name": "qft", "n": n, "ops": C.qft_ops(n, x), "initial_seed": None,
+            "run": {"shots": None, "seed": None, "returns": None}}
+    circ = C.build(Circuit, case)
+    got = circ.run(backend=backend)
+    assert maxabs(got, _oracle(circ)) <= TOL
+    y = np.arange(1 << n, dtype=np.int64)
+    analytic = np.exp(2j * np.pi * ((x * y) % (1 << n)) / (1 << n)) / np.sqrt(1 << n)
+    assert maxabs(got, analytic) <= 1e-11
+
+
+@pytest.mark.parametrize("n", [14, 20])
+def test_c3_qaoa_energy(n, backend):
+    ops, edges = C.qaoa_ops(n)
+    case = {"name": "qaoa", "n": n, "ops": ops, "initial_seed": None,
+            "run": {"shots": None, "seed": None, "returns": None}}
+    circ = C.build(Circuit, case)
+    h = sum((Z[i] * Z[j] for i, j in edges[1:]), Z[edges[0][0]] * Z[edges[0][1]])
+    psi = _oracle(circ)
+    want = O.expectation([(1.0, [("Z", i), ("Z", j)]) for i, j in edges], psi)
+    assert abs(circ.run(backend=backend, hamiltonian=h) - want) < 1e-10
+    assert maxabs(circ.run(backend=backend), psi) <= TOL
+
+
+def test_midcircuit_and_reset_against_oracle(backend):
+    rng = np.random.default_rng(99)
+    for n in (3, 6, 10):
+        ops = C.random_ops(rng, n, 40, False) + [C._op("m", 0)] + C.random_ops(rng, n, 20, False) + \
+            [C._op("reset", n - 1)] + C.random_ops(rng, n, 10, False) + [C._op("m", slice(None))]
+        case = {"name": "mid", "n": n, "ops": ops, "initial_seed": None,
+                "run": {"shots": 60, "seed": 5, "returns": "statevector_and_shots"}}
+        circ = C.build(Circuit, case)
+        random.seed(5)
+        rsv, rcnt = _oracle(circ, shots=60, returns="statevector_and_shots")
+        gsv, gcnt = run_case(case, backend)
+        assert gcnt == rcnt
+        assert maxabs(gsv, rsv) <= TOL
+
+
+def test_size_independent_properties_at_scale(backend):
+    """26 qubits (1 GiB): norm preservation, U then U^dagger returns |0..0>, GHZ shots."""
+    n = 26
+    case = {"name": "big", "n": n, "ops": C.random_layer_ops(n, 4), "initial_seed": None,
+            "run": {"shots": None, "seed": None, "returns": None}}
+    circ = C.build(Circuit, case)
+    both = circ + circ.dagger()
+    ctx = both.run(backend=backend, returns="_inner_ctx")
+    st = ctx.device_state
+    assert abs(st.norm2() - 1.0) < 1e-10
+    idx, amp = st.first_above(0.5)
+    assert idx == 0 and abs(amp - 1.0) < 1e-10
+    ghz = Circuit(n).h[0]
+    for q in range(n - 1):
+        ghz.cx[q, q + 1]
+    random.seed(1)
+    cnt = ghz.m[:].run(backend=backend, shots=50)
+    assert set(cnt) <= {"0" * n, "1" * n} and sum(cnt.values()) == 50
+
+
+def test_backend_requires_the_cuda_library(monkeypatch):
+    """No silent CPU fallback: a missing library is a hard error."""
+    from qaqarot_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libb200sv.so")
+    with pytest.raises(_lib.B200LibraryError):
+        B200Backend().run(Circuit().h[0].ops, 1)

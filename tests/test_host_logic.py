@@ -1,0 +1,172 @@
+"""Host-side logic on a CPU: lowering, program encoding, shot descent, cache handling, kwargs.
+
+The device is replaced by oracle/program_interp.OracleState, an independent numpy executor of the encoded op
+program, so these tests pin everything above the C ABI against the reference fixtures without a GPU.
+"""
+import random
+import warnings
+from collections import Counter
+
+import numpy as np
+import pytest
+
+from conftest import case_names
+from helpers import TOL, cpu_backend, maxabs, run_case
+from qaqarot_b200 import Circuit, X, Y, Z
+from qaqarot_b200.pauli import canonical_terms
+
+MODES = [False, True]
+
+
+@pytest.mark.parametrize("fusion", MODES)
+@pytest.mark.parametrize("name", case_names("statevector"))
+def test_statevector_cases(name, fusion, gold):
+    out = run_case(gold.cases[name], cpu_backend(fusion))
+    assert maxabs(out, gold.sv(name)) <= TOL
+
+
+@pytest.mark.parametrize("fusion", MODES)
+@pytest.mark.parametrize("name", case_names("shots"))
+def test_shot_cases(name, fusion, gold):
+    out = run_case(gold.cases[name], cpu_backend(fusion))
+    assert dict(out) == gold.meta["cases"][name]["shots"]
+
+
+@pytest.mark.parametrize("fusion", MODES)
+def test_statevector_and_shots(fusion, gold):
+    sv, cnt = run_case(gold.cases["sv_and_shots"], cpu_backend(fusion))
+    assert dict(cnt) == gold.meta["cases"]["sv_and_shots"]["shots"]
+    assert maxabs(sv, gold.sv("sv_and_shots")) <= TOL
+
+
+def test_samples(gold):
+    assert run_case(gold.cases["samples_keys"], cpu_backend()) == gold.meta["cases"]["samples_keys"]["samples"]
+
+
+@pytest.mark.parametrize("fusion", MODES)
+def test_hamiltonian_kwarg(fusion, gold):
+    letter = {"X": X, "Y": Y, "Z": Z}
+    for name, recs in gold.meta["expect"].items():
+        for rec in recs:
+            h = 0
+            for coeff, letters in rec["terms"]:
+                t = coeff
+                for ch, q in letters:
+                    t = t * letter[ch][q]
+                h = h + t
+            import cases as C
+            circ = C.build(Circuit, gold.cases[name])
+            init = C.initial_state(gold.cases[name])
+            kw = {} if init is None else {"initial": init}
+            val = circ.run(backend=cpu_backend(fusion), hamiltonian=h, **kw)
+            assert isinstance(val, float)
+            assert abs(val - rec["value"]) < 1e-10
+
+
+def test_readme_known_answers():
+    """README.md:83-89 and :72-76 of the reference."""
+    assert Circuit(4).x[:].run(backend=cpu_backend(), hamiltonian=1 * Z[0] + 1 * Z[1]) == pytest.approx(-2.0)
+    assert Circuit(20).x[:].m[:].run(backend=cpu_backend(), shots=100) == Counter({"1" * 20: 100})
+
+
+def test_run_argument_handling():
+    be = cpu_backend()
+    c = Circuit().h[0].cx[0, 1]
+    with pytest.raises(ValueError):
+        c.run(backend=be, returns="nope")
+    with pytest.warns(UserWarning):
+        c.run(backend=be, foo=1)
+    with pytest.warns(UserWarning):
+        c.run(backend=be, shots=5, returns="statevector")
+    with pytest.raises(ValueError):
+        c.run(backend=be, initial=[1, 0, 0, 0])
+    with pytest.raises(ValueError):
+        c.run(backend=be, initial=np.array([1, 0]))
+    assert c.run(backend=be, shots=7) == Counter({"00": 7})
+    assert sum(Circuit().h[0].m[0].run(backend=be, returns="shots").values()) == 1024
+    assert np.allclose(Circuit().run(backend=be), [1])
+    assert Circuit().run(backend=be, shots=3) == Counter()
+    v, s = Circuit().x[1].m[:].oneshot(backend=be)
+    assert s == "01" and np.allclose(v, [0, 0, 1, 0])
+    assert np.allclose(Circuit().x[0].statevector(backend=be), [0, 1])
+    assert Circuit().x[0].m[0].shots(10, backend=be) == Counter({"1": 10})
+
+
+def test_unknown_operation():
+    class Weird:
+        lowername = "weird"
+        targets = 0
+    with pytest.raises(ValueError):
+        cpu_backend().run([Weird()], 1)
+
+
+def test_cache_semantics():
+    """save_cache / make_cache resume from the pre-measurement snapshot (numpy_backend.py:564-568, 610-626)."""
+    be = cpu_backend()
+    c = Circuit().h[0].cx[0, 1].m[:]
+    c._backends["b200"] = be
+    assert be.cache is None and be.cache_idx == -1
+    c.make_cache(backend="b200")
+    assert be.cache is not None and be.cache_idx == 1
+    random.seed(3)
+    got = c.run(backend="b200", shots=50)
+    assert set(got) <= {"00", "11"} and sum(got.values()) == 50
+    # appending after caching keeps working (tests/test_circuit.py: test_cache_then_append)
+    c.x[1].m[1]
+    got = c.run(backend="b200", shots=20)
+    assert set(got) <= {"01", "10"} and be.cache is not None
+    c2 = c.copy()
+    assert c2._backends["b200"].cache is not None and c2._backends["b200"] is not be
+    # a different qubit count invalidates the snapshot
+    d = Circuit().x[0].m[0]
+    d._backends["b200"] = be
+    assert d.run(backend="b200", shots=3) == Counter({"1": 3})
+    assert be.cache is None
+
+
+def test_initial_disables_cache():
+    be = cpu_backend()
+    c = Circuit().h[0].m[0]
+    init = np.array([0, 1], dtype=complex)
+    with pytest.warns(UserWarning):
+        c.run(backend=be, initial=init, save_cache=True, shots=2)
+    assert be.cache is None
+
+
+def test_ignore_global():
+    be = cpu_backend()
+    v = Circuit().x[0].rz(1.0)[0].run(backend=be, ignore_global=True)
+    assert np.allclose(v, [0, 1])
+
+
+def test_canonical_terms_accepts_mirror_algebra():
+    h = 2 * X[0] * Y[1] - Z[2] + 0.5 * X[0] * X[0]
+    terms = {tuple(l): c for c, l in canonical_terms(h)}
+    assert terms[(("X", 0), ("Y", 1))] == 2
+    assert terms[(("Z", 2),)] == -1
+    assert terms[()] == 0.5
+
+
+@pytest.mark.reference
+def test_blueqat_objects_are_accepted():
+    """The same backend instance consumes genuine blueqat operations and pauli expressions."""
+    import sys
+    sys.path.insert(0, "/root/reference")
+    warnings.simplefilter("ignore", SyntaxWarning)
+    import blueqat
+    from blueqat import pauli
+    import qaqarot_b200
+    qaqarot_b200.register()
+    assert "b200" in blueqat.backends.BACKENDS
+    c = blueqat.Circuit().h[0].cx[0, 1].rz(0.3)[1].ccx[0, 1, 2].swap[0, 2].rxx(0.2)[0, 1].m[:]
+    be = cpu_backend()
+    random.seed(11)
+    ref = c.run(backend="numpy", shots=40)
+    random.seed(11)
+    assert c.run(backend=be, shots=40) == ref
+    c2 = blueqat.Circuit().h[:3].cx[0, 1].ry(0.4)[2].cz[1, 2]
+    assert maxabs(c2.run(backend=be), c2.run(backend="numpy")) <= TOL
+    h = 1.5 * pauli.Z[0] * pauli.Z[1] + pauli.X[2] - 0.3 * pauli.Y[0] * pauli.X[1]
+    from blueqat import vqe
+    ref_e = vqe.sparse_expectation(h.to_expr().simplify().to_matrix(3, sparse="csc"), c2.run(backend="numpy"))
+    assert abs(c2.run(backend=be, hamiltonian=h) - ref_e) < 1e-12
