@@ -111,6 +111,17 @@ int b200_expect_group(b200_state* st, uint64_t xmask, int n_terms, const uint64_
 
 int b200_sync(b200_state* st);
 
+/* ---- measurement support for bench.py / profiling ------------------------------------------------ */
+
+/* Record CUDA event `slot` (0..15) on the state's stream; elapsed device time between two recorded slots. */
+int b200_event_record(b200_state* st, int slot);
+int b200_event_elapsed_ms(b200_state* st, int slot_a, int slot_b, double* ms);
+
+/* Page-locked host memory for upload/download staging (the reference returns a host ndarray;
+   a pinned destination lets b200_state_download run at PCIe rate). */
+int b200_host_alloc(size_t bytes, void** out);
+int b200_host_free(void* p);
+
 #ifdef __cplusplus
 }
 #endif

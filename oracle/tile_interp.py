@@ -1,0 +1,106 @@
+"""numpy interpreter of one fused tile pass descriptor.  TEST INFRASTRUCTURE -- never imported by the product.
+
+Executes exactly the words / reals that cross the C ABI for a ``B200_OP_TILE`` op (format: csrc/tile.cu and
+qaqarot_b200/planner.py::encode_pass), gate by gate on the whole state, evaluating masks, fan tables and
+fixed-bit products the way the CUDA kernel does per thread.  It also checks the structural promises the
+kernel relies on (tile bits ascending with the low `c` bits contiguous, orders being permutations, payload
+offsets in range).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+K_MAT, K_X, K_PHASE, K_FAN = 1, 2, 3, 4
+F_REAL = 1
+
+
+def _unpack8(lo: int, hi: int, count: int):
+    v = [(lo >> (8 * i)) & 0xFF for i in range(8)] + [(hi >> (8 * i)) & 0xFF for i in range(8)]
+    return v[:count]
+
+
+def _pext(idx: np.ndarray, positions) -> np.ndarray:
+    out = np.zeros_like(idx)
+    for i, p in enumerate(positions):
+        out |= ((idx >> np.uint64(p)) & np.uint64(1)) << np.uint64(i)
+    return out
+
+
+def run_tile_pass(psi: np.ndarray, n: int, words: np.ndarray, reals: np.ndarray, index_offset: int = 0) -> None:
+    w = [int(x) for x in words]
+    a, c, r = w[0] & 0xFF, (w[0] >> 8) & 0xFF, (w[0] >> 16) & 0xFF
+    n_rounds, n_fans = (w[0] >> 24) & 0xFF, (w[0] >> 32) & 0xFF
+    tile = _unpack8(w[1], w[2], a)
+    assert a <= n and tile == sorted(set(tile)) and tile[:c] == list(range(c)) and all(q < n for q in tile)
+    dir_off, rounds_off = w[3] & 0xFFFFFFFF, w[3] >> 32
+    cre = reals.view(np.complex128) if reals.size % 2 == 0 else reals[:-1].view(np.complex128)
+
+    def cplx(roff, count=1):
+        assert roff % 2 == 0 and roff // 2 + count <= cre.size, "payload offset out of range"
+        return cre[roff // 2: roff // 2 + count]
+
+    idx = np.arange(psi.size, dtype=np.uint64)
+    tile_mask = sum(1 << q for q in tile)
+    fixed = (idx | np.uint64(index_offset)) & ~np.uint64(tile_mask)
+    local = _pext(idx, tile)
+
+    # per-tile fixed products of every fan (the kernel computes these once per tile in its setup phase)
+    fan_fixed = []
+    for f in range(n_fans):
+        off = w[dir_off + f]
+        n_e, roff = w[off] & 0xFFFFFFFF, w[off] >> 32
+        ws = cplx(roff, 1 + n_e)
+        val = np.full(psi.size, ws[0], dtype=complex)
+        for e in range(n_e):
+            m = np.uint64(w[off + 1 + e])
+            val = np.where((fixed & m) == m, val * ws[1 + e], val)
+        fan_fixed.append(val)
+
+    pos = rounds_off
+    for _ in range(n_rounds):
+        n_gates, n_words = w[pos] & 0xFFFF, w[pos] >> 16
+        order = _unpack8(w[pos + 1], w[pos + 2], a)
+        assert sorted(order) == list(range(a)), "round order is not a permutation of the local bits"
+        rho = _pext(local, order[:r])
+        tid = _pext(local, order[r:])
+        lane, warp = tid & np.uint64(31), tid >> np.uint64(5)
+        g = pos + 3
+        for _g in range(n_gates):
+            g0, fm, roff = w[g], np.uint64(w[g + 1]), w[g + 2]
+            g += 3
+            kind, j, flags, fid = g0 & 0xFF, (g0 >> 8) & 0xFF, (g0 >> 16) & 0xFF, (g0 >> 24) & 0xFF
+            lm, rm = np.uint64((g0 >> 32) & 0xFFFF), np.uint64((g0 >> 48) & 0xFFFF)
+            cond = ((fixed & fm) == fm) & ((local & lm) == lm)
+            if kind in (K_MAT, K_X):
+                assert j < r
+                cond &= (rho & rm) == rm
+                tbit = np.uint64(1 << tile[order[j]])
+                i0 = idx[cond & ((idx & tbit) == 0)]
+                i1 = i0 | tbit
+                a0, a1 = psi[i0], psi[i1]
+                if kind == K_X:
+                    psi[i0], psi[i1] = a1, a0
+                else:
+                    m = cplx(roff, 4)
+                    if flags & F_REAL:
+                        assert np.all(m.imag == 0)
+                    psi[i0] = m[0] * a0 + m[1] * a1
+                    psi[i1] = m[2] * a0 + m[3] * a1
+            elif kind == K_PHASE:
+                cond &= (rho & rm) == rm
+                psi[cond] *= cplx(roff)[0]
+            elif kind == K_FAN:
+                nt = a - r
+                n_warp = 1 << max(0, nt - 5)
+                tab = cplx(roff, 32 + n_warp + (1 << r))
+                lane_t, warp_t, reg_t = tab[:32], tab[32:32 + n_warp], tab[32 + n_warp:]
+                skip = int(rm)
+                keep = cond & (((np.uint64(skip) >> rho) & np.uint64(1)) == 0)
+                factor = fan_fixed[fid] * lane_t[lane.astype(np.int64)] * warp_t[warp.astype(np.int64)] \
+                    * reg_t[rho.astype(np.int64)]
+                psi[keep] *= factor[keep]
+            else:
+                raise ValueError(f"unknown tile gate kind {kind}")
+        assert g == pos + n_words, "round length mismatch"
+        pos += n_words
+    assert pos == len(w), "descriptor length mismatch"

@@ -65,6 +65,10 @@ _SIGNATURES = {
     "b200_expect_group": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                     _P(C.c_double), _P(C.c_double)]),
     "b200_sync": (C.c_int, [C.c_void_p]),
+    "b200_event_record": (C.c_int, [C.c_void_p, C.c_int]),
+    "b200_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _P(C.c_double)]),
+    "b200_host_alloc": (C.c_int, [C.c_size_t, _P(C.c_void_p)]),
+    "b200_host_free": (C.c_int, [C.c_void_p]),
 }
 EXPORTS: List[str] = sorted(_SIGNATURES)
 

@@ -107,21 +107,29 @@ def _check_initial(initial, n_qubits: int) -> np.ndarray:
 class B200Backend(_Base):
     """Statevector simulator backend running on one NVIDIA B200 through libb200sv.so."""
 
-    def __init__(self, device: int = 0, fusion: bool = True, state_factory=None, planner=None):
+    def __init__(self, device: int = 0, fusion: bool = True, state_factory=None, planner=None, plan_config=None):
         self.device = device
         self.fusion = fusion
+        self.plan_config = plan_config
         self.cache = None                    # device snapshot taken before the first Measurement/Reset
         self.cache_idx = -1
         self._state_factory = state_factory or _default_state_factory
         if planner is None:
-            if fusion:
+            if fusion and plan_config is not None:
+                from .planner import plan as _plan
+                planner = lambda prims, n, _cfg=plan_config: _plan(prims, n, _cfg)
+            elif fusion:
                 from .planner import plan as planner
             else:
-                planner = lambda prims, n: unfused_program(prims)
+                planner = lambda prims, n: unfused_program(prims, n)
         self._planner = planner
         self._work = None                    # reusable work state
         self._compiled: Optional[_Compiled] = None
         self.last_stats: Dict[str, Any] = {}
+        # optional caller-provided host destination for returned statevectors (e.g. a page-locked buffer,
+        # device.PinnedBuffer): like the reference, which returns its live context array, the result is then
+        # only valid until the next run on this backend.
+        self.result_buffer: Optional[np.ndarray] = None
 
     # -- Backend protocol -------------------------------------------------------------------------
     def copy(self) -> "B200Backend":
@@ -159,6 +167,12 @@ class B200Backend(_Base):
         if c is None or not c.matches(gates, n_qubits, start):
             c = self._compiled = _Compiled(gates, n_qubits, start, self._planner)
         return c
+
+    def _download(self, st) -> np.ndarray:
+        buf = self.result_buffer
+        if buf is not None and buf.size == st.dim and buf.dtype == np.complex128 and buf.flags.c_contiguous:
+            return st.download(out=buf)
+        return st.download()
 
     # -- the run loop -----------------------------------------------------------------------------
     def _execute(self, gates, n_qubits, shots: int, initial, save_cache: bool, want_final_state: bool,
@@ -327,7 +341,7 @@ class B200Backend(_Base):
         st = ctx.device_state
         if ignore_global:
             _ignore_global_phase(st)
-        ctx.qubits = st.download()
+        ctx.qubits = self._download(st)
         if returns == "statevector":
             return ctx.qubits
         if returns == "statevector_and_shots":

@@ -303,6 +303,7 @@ int b200_state_destroy(b200_state* st) {
   if (st->prog.start) cudaEventDestroy(st->prog.start);
   if (st->prog.stop) cudaEventDestroy(st->prog.stop);
   for (cudaEvent_t e : st->op_events) cudaEventDestroy(e);
+  for (cudaEvent_t e : st->user_events) if (e) cudaEventDestroy(e);
   if (st->stream) cudaStreamDestroy(st->stream);
   delete st;
   return 0;
@@ -653,6 +654,38 @@ int b200_expect_group(b200_state* st, uint64_t xmask, int n_terms, const uint64_
     *out_re += st->h_result[0];
     *out_im += st->h_result[1];
   }
+  return 0;
+}
+
+int b200_event_record(b200_state* st, int slot) {
+  B200_REQUIRE(st != nullptr, "b200_event_record: null state");
+  B200_REQUIRE(slot >= 0 && slot < 16, "b200_event_record: slot out of range [0, 16)");
+  B200_CUDA(cudaSetDevice(st->device));
+  if (!st->user_events[slot]) B200_CUDA(cudaEventCreate(&st->user_events[slot]));
+  B200_CUDA(cudaEventRecord(st->user_events[slot], st->stream));
+  return 0;
+}
+
+int b200_event_elapsed_ms(b200_state* st, int slot_a, int slot_b, double* ms) {
+  B200_REQUIRE(st != nullptr && ms != nullptr, "b200_event_elapsed_ms: null argument");
+  B200_REQUIRE(slot_a >= 0 && slot_a < 16 && slot_b >= 0 && slot_b < 16, "b200_event_elapsed_ms: slot out of range");
+  B200_REQUIRE(st->user_events[slot_a] && st->user_events[slot_b], "b200_event_elapsed_ms: slot never recorded");
+  B200_CUDA(cudaSetDevice(st->device));
+  B200_CUDA(cudaEventSynchronize(st->user_events[slot_b]));
+  float f = 0.f;
+  B200_CUDA(cudaEventElapsedTime(&f, st->user_events[slot_a], st->user_events[slot_b]));
+  *ms = f;
+  return 0;
+}
+
+int b200_host_alloc(size_t bytes, void** out) {
+  B200_REQUIRE(out != nullptr, "b200_host_alloc: null out");
+  B200_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return 0;
+}
+
+int b200_host_free(void* p) {
+  if (p) B200_CUDA(cudaFreeHost(p));
   return 0;
 }
 

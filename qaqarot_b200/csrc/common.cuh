@@ -23,6 +23,7 @@ struct b200_state {
   int device = 0;
   int n = 0;                       // qubits held in this buffer (a shard when used multi-GPU)
   uint64_t dim = 1;                // 2^n
+  uint64_t index_offset = 0;       // index bits above n (the shard's rank bits), seen by controls and phases
   b200::c128* amp = nullptr;       // device amplitudes
   bool owns = true;
   cudaStream_t stream = nullptr;
@@ -38,6 +39,7 @@ struct b200_state {
   std::vector<cudaEvent_t> op_events;      // 2 per op while profiling
   std::vector<int32_t> op_kinds;
   uint64_t launches = 0;
+  cudaEvent_t user_events[16] = {};
 };
 
 namespace b200 {

@@ -1,11 +1,311 @@
-// tile.cu -- fused tile-resident multi-gate pass (placeholder until the kernel lands).
+// tile.cu -- the fused tile-resident multi-gate pass (B200_OP_TILE), sm_100a.
+//
+// One pass = one read and one write of the state (32 * 2^n bytes, the HBM-bound unit of SURVEY.md 8(d)), with
+// as many gates as the planner could legally bring onto the tile applied on chip in between.
+//
+// Data layout.  A pass owns A index bits `tile[0..A)` (ascending physical positions; tile[i] = i for i < c so
+// that 2^c amplitudes = 2^c * 16 B are contiguous in HBM).  Tile number t in [0, 2^(n-A)) has its bits spread
+// over the remaining index positions; a CTA copies the 2^A amplitudes of its tile to shared memory with
+// 16-byte cp.async (coalesced rows), runs the pass's rounds, and streams the tile back with 16-byte stores.
+// Shared-memory slot of local index l is swz(l) = l ^ xor of l's higher 3-bit groups folded into bits 0..2:
+// GF(2)-linear, so swz(thread part | register part) = swz(thread) ^ swz(register), and a quarter warp's eight
+// 16-byte accesses fall into eight different 16-byte bank groups whenever the thread bits mapped to lane bits
+// 0..2 have distinct positions mod 3 (the planner orders them so).
+//
+// Rounds.  In a round every thread holds 2^R amplitudes in registers: the R *register bits* (local bit
+// positions order[0..R)) enumerate them, the thread index supplies the other A-R local bits through
+// order[R..A).  Non-diagonal gates act on register bits only, so a 2x2 gate is pure register arithmetic
+// (complex128 FMA chains, target position resolved to a compile-time template by a warp-uniform switch);
+// controls and phases may involve any bit: register bits become compile-time lane-invariant predicates,
+// thread bits a per-thread predicate, bits outside the tile a per-tile (CTA-uniform) predicate.
+//
+// Descriptor (uint64 words, produced by qaqarot_b200/planner.py::encode_pass; `reals` = float64 pool):
+//   D[0] = A | c<<8 | R<<16 | n_rounds<<24 | n_fans<<32          D[1], D[2] = tile bit positions, 8 bits each
+//   D[3] = fan directory offset | rounds offset << 32
+//   fan directory: n_fans word offsets; fan record: n_entries | roff<<32, then n_entries masks.
+//       reals[roff] = w0, then one complex per entry.  Per tile: fix[f] = w0 * prod{w_e : mask_e subset of index}
+//   round: n_gates | n_words<<16, order[0..8), order[8..16), then 3 words per gate:
+//       G0 = kind | j<<8 | flags<<16 | fan<<24 | thread_mask<<32 | reg_mask<<48,  G1 = fixed-bit mask,  G2 = roff
+//     MAT  (1): 2x2 (reals[roff..+8), row major re/im) on register bit j where all masks are satisfied
+//     X    (2): pair swap on register bit j under the masks
+//     PHASE(3): amp *= reals[roff] where all masks are satisfied
+//     FAN  (4): amp *= fix[fan] * lane_t[lane] * warp_t[warp] * reg_t[rho] unless bit rho of reg_mask is set
+//               (tables at roff: 32 + 2^(A-R-5) + 2^R complex); thread_mask / fixed mask select the fan target
 #include "common.cuh"
+
+#include <cstdio>
 
 namespace b200 {
 
-int launch_tile_pass(b200_state*, const uint64_t*, const uint64_t*, int, const double*) {
-  set_error("B200_OP_TILE: fused tile pass is not built into this library");
-  return 1;
+constexpr int kMaxFans = 64;
+constexpr int K_MAT = 1, K_X = 2, K_PHASE = 3, K_FAN = 4;
+
+__device__ __forceinline__ uint32_t swz(uint32_t l) {
+  return l ^ ((l >> 3) & 7u) ^ ((l >> 6) & 7u) ^ ((l >> 9) & 7u) ^ ((l >> 12) & 7u);
+}
+__host__ __device__ constexpr uint32_t swz_c(uint32_t l) {
+  return l ^ ((l >> 3) & 7u) ^ ((l >> 6) & 7u) ^ ((l >> 9) & 7u) ^ ((l >> 12) & 7u);
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+__device__ __forceinline__ int byte_of(uint64_t lo, uint64_t hi, int i) {
+  return (int)(((i < 8 ? lo : hi) >> (8 * (i & 7))) & 0xFF);
+}
+
+// ---- register-resident gate bodies (J = register bit, compile time) ---------------------------------------
+template <int R, int J>
+__device__ __forceinline__ void mat_c(c128 (&v)[1 << R], const double* __restrict__ m, uint32_t rm) {
+  const c128 m00 = make_double2(m[0], m[1]), m01 = make_double2(m[2], m[3]);
+  const c128 m10 = make_double2(m[4], m[5]), m11 = make_double2(m[6], m[7]);
+#pragma unroll
+  for (int rho = 0; rho < (1 << R); ++rho) {
+    if (rho & (1 << J)) continue;
+    if ((rho & rm) == rm) {
+      const c128 a0 = v[rho], a1 = v[rho | (1 << J)];
+      v[rho] = cfma(m01, a1, cmul(m00, a0));
+      v[rho | (1 << J)] = cfma(m11, a1, cmul(m10, a0));
+    }
+  }
+}
+template <int R, int J>
+__device__ __forceinline__ void mat_r(c128 (&v)[1 << R], const double* __restrict__ m, uint32_t rm) {
+  const double m00 = m[0], m01 = m[2], m10 = m[4], m11 = m[6];
+#pragma unroll
+  for (int rho = 0; rho < (1 << R); ++rho) {
+    if (rho & (1 << J)) continue;
+    if ((rho & rm) == rm) {
+      const c128 a0 = v[rho], a1 = v[rho | (1 << J)];
+      v[rho] = make_double2(fma(m01, a1.x, m00 * a0.x), fma(m01, a1.y, m00 * a0.y));
+      v[rho | (1 << J)] = make_double2(fma(m11, a1.x, m10 * a0.x), fma(m11, a1.y, m10 * a0.y));
+    }
+  }
+}
+template <int R, int J>
+__device__ __forceinline__ void perm_x(c128 (&v)[1 << R], uint32_t rm) {
+#pragma unroll
+  for (int rho = 0; rho < (1 << R); ++rho) {
+    if (rho & (1 << J)) continue;
+    if ((rho & rm) == rm) {
+      const c128 a0 = v[rho];
+      v[rho] = v[rho | (1 << J)];
+      v[rho | (1 << J)] = a0;
+    }
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void apply_target(c128 (&v)[1 << R], int kind, bool real, int j, const double* m,
+                                             uint32_t rm) {
+#define B200_CASE(J)                                            \
+  case J:                                                       \
+    if (J < R) {                                                \
+      if (kind == K_X) perm_x<R, (J < R ? J : 0)>(v, rm);       \
+      else if (real) mat_r<R, (J < R ? J : 0)>(v, m, rm);       \
+      else mat_c<R, (J < R ? J : 0)>(v, m, rm);                 \
+    }                                                           \
+    break;
+  switch (j) {
+    B200_CASE(0) B200_CASE(1) B200_CASE(2) B200_CASE(3) B200_CASE(4)
+    default: break;
+  }
+#undef B200_CASE
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------------------
+template <int A, int R, int MINB>
+__global__ void __launch_bounds__(1 << (A - R), MINB)
+k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const uint64_t* __restrict__ desc,
+       const double* __restrict__ reals) {
+  constexpr int NT = 1 << (A - R), PER = 1 << R, NTB = A - R;
+  constexpr int NWARP_T = (NTB > 5) ? (1 << (NTB - 5)) : 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  c128* sm = reinterpret_cast<c128*>(smem_raw);
+  c128* fix = sm + (1 << A);
+
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint64_t h0 = desc[0], tb_lo = desc[1], tb_hi = desc[2];
+  const int n_rounds = (int)((h0 >> 24) & 0xFF), n_fans = (int)((h0 >> 32) & 0xFF);
+  const uint32_t dir_off = (uint32_t)(desc[3] & 0xFFFFFFFFu), rounds_off = (uint32_t)(desc[3] >> 32);
+
+  // copy phases: thread handles local indices l = i * NT + tid; off_t / hb[] deposit l into index positions
+  uint64_t off_t = 0;
+#pragma unroll
+  for (int b = 0; b < NTB; ++b) off_t |= (uint64_t)((tid >> b) & 1u) << byte_of(tb_lo, tb_hi, b);
+  uint64_t hb[R];
+#pragma unroll
+  for (int k = 0; k < R; ++k) hb[k] = 1ull << byte_of(tb_lo, tb_hi, NTB + k);
+  const uint32_t sw_t = swz(tid);
+
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    uint64_t base = tile;
+#pragma unroll
+    for (int i = 0; i < A; ++i) base = insert_zero(base, byte_of(tb_lo, tb_hi, i));
+    const uint64_t fixedidx = base | index_offset;
+    c128* __restrict__ g = amp + base + off_t;
+
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      uint64_t off = 0;
+#pragma unroll
+      for (int k = 0; k < R; ++k)
+        if ((i >> k) & 1) off |= hb[k];
+      cp_async16(&sm[sw_t ^ swz_c((uint32_t)i * NT)], g + off);
+    }
+
+    // per-tile fixed-bit products of the fans, while the copies are in flight (one warp per fan)
+    for (int f = (int)warp; f < n_fans; f += (NT >> 5)) {
+      const uint32_t off = (uint32_t)desc[dir_off + f];
+      const uint64_t rec = desc[off];
+      const int ne = (int)(rec & 0xFFFFFFFFu);
+      const double2* __restrict__ w = reinterpret_cast<const double2*>(reals + (rec >> 32));
+      c128 p = make_double2(1.0, 0.0);
+      for (int e = (int)lane; e < ne; e += 32) {
+        const uint64_t m = desc[off + 1 + e];
+        if ((fixedidx & m) == m) p = cmul(p, w[1 + e]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        c128 q;
+        q.x = __shfl_xor_sync(0xffffffffu, p.x, o);
+        q.y = __shfl_xor_sync(0xffffffffu, p.y, o);
+        p = cmul(p, q);
+      }
+      if (lane == 0) fix[f] = cmul(p, w[0]);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    const uint64_t* __restrict__ rp = desc + rounds_off;
+    for (int rd = 0; rd < n_rounds; ++rd) {
+      const uint64_t rh = rp[0], o_lo = rp[1], o_hi = rp[2];
+      const int ng = (int)(rh & 0xFFFF);
+      uint32_t lt = 0;
+#pragma unroll
+      for (int b = 0; b < NTB; ++b) lt |= ((tid >> b) & 1u) << byte_of(o_lo, o_hi, R + b);
+      uint32_t sr[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) sr[k] = swz(1u << byte_of(o_lo, o_hi, k));
+      const uint32_t st = swz(lt);
+
+      c128 v[PER];
+#pragma unroll
+      for (int rho = 0; rho < PER; ++rho) {
+        uint32_t s = st;
+#pragma unroll
+        for (int k = 0; k < R; ++k)
+          if ((rho >> k) & 1) s ^= sr[k];
+        v[rho] = sm[s];
+      }
+
+      const uint64_t* __restrict__ gp = rp + 3;
+      for (int gi = 0; gi < ng; ++gi, gp += 3) {
+        const uint64_t g0 = gp[0], fm = gp[1];
+        if ((fixedidx & fm) != fm) continue;                       // CTA-uniform
+        const double* __restrict__ pay = reals + gp[2];
+        const int kind = (int)(g0 & 0xFF);
+        const uint32_t lm = (uint32_t)((g0 >> 32) & 0xFFFF), rm = (uint32_t)((g0 >> 48) & 0xFFFF);
+        if ((lt & lm) != lm) continue;                             // per thread
+        if (kind == K_MAT || kind == K_X) {
+          apply_target<R>(v, kind, ((g0 >> 16) & 1) != 0, (int)((g0 >> 8) & 0xFF), pay, rm);
+        } else if (kind == K_PHASE) {
+          const c128 w = make_double2(pay[0], pay[1]);
+#pragma unroll
+          for (int rho = 0; rho < PER; ++rho)
+            if ((rho & rm) == rm) v[rho] = cmul(v[rho], w);
+        } else if (kind == K_FAN) {
+          const double2* __restrict__ tab = reinterpret_cast<const double2*>(pay);
+          const c128 wt = cmul(fix[(g0 >> 24) & 0xFF], cmul(tab[lane], tab[32 + (NWARP_T > 1 ? warp : 0)]));
+#pragma unroll
+          for (int rho = 0; rho < PER; ++rho)
+            if (!((rm >> rho) & 1u)) v[rho] = cmul(v[rho], cmul(wt, tab[32 + NWARP_T + rho]));
+        }
+      }
+
+#pragma unroll
+      for (int rho = 0; rho < PER; ++rho) {
+        uint32_t s = st;
+#pragma unroll
+        for (int k = 0; k < R; ++k)
+          if ((rho >> k) & 1) s ^= sr[k];
+        sm[s] = v[rho];
+      }
+      __syncthreads();
+      rp += (rh >> 16);
+    }
+
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      uint64_t off = 0;
+#pragma unroll
+      for (int k = 0; k < R; ++k)
+        if ((i >> k) & 1) off |= hb[k];
+      g[off] = sm[sw_t ^ swz_c((uint32_t)i * NT)];
+    }
+    __syncthreads();     // the next tile's cp.async must not overwrite slots still being read
+  }
+}
+
+template <int A, int R, int MINB>
+static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals) {
+  constexpr int NT = 1 << (A - R);
+  const size_t smem = sizeof(c128) * ((size_t(1) << A) + kMaxFans);
+  static bool configured[64] = {};
+  if (!configured[st->device & 63]) {
+    B200_CUDA(cudaFuncSetAttribute(k_tile<A, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[st->device & 63] = true;
+  }
+  const uint64_t n_tiles = st->dim >> A;
+  const uint64_t cap = (uint64_t)kSMs * 64;
+  const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
+  k_tile<A, R, MINB><<<grid, NT, smem, st->stream>>>(st->amp, n_tiles, st->index_offset, d_desc, d_reals);
+  st->launches++;
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_desc, int wlen,
+                     const double* d_reals) {
+  B200_REQUIRE(wlen >= 4, "TILE descriptor too short");
+  const uint64_t h0 = h_desc[0];
+  const int A = (int)(h0 & 0xFF), c = (int)((h0 >> 8) & 0xFF), R = (int)((h0 >> 16) & 0xFF);
+  const int n_fans = (int)((h0 >> 32) & 0xFF);
+  char msg[200];
+  if (A > st->n || c > A || R != 4 || n_fans > kMaxFans) {
+    snprintf(msg, sizeof msg, "TILE descriptor not executable: A=%d c=%d R=%d fans=%d on %d qubits", A, c, R, n_fans,
+             st->n);
+    set_error(msg);
+    return 1;
+  }
+  int prev = -1;
+  for (int i = 0; i < A; ++i) {
+    const int b = (int)(((i < 8 ? h_desc[1] : h_desc[2]) >> (8 * (i & 7))) & 0xFF);
+    if (b <= prev || b >= st->n || (i < c && b != i)) {
+      set_error("TILE descriptor: tile bits must be ascending, below n_qubits, and 0..c-1 first");
+      return 1;
+    }
+    prev = b;
+  }
+  const uint64_t dir_off = h_desc[3] & 0xFFFFFFFFu, rounds_off = h_desc[3] >> 32;
+  B200_REQUIRE(dir_off + (uint64_t)n_fans <= (uint64_t)wlen && rounds_off <= (uint64_t)wlen,
+               "TILE descriptor: offsets out of range");
+  switch (A) {
+    case 9:  return launch<9, 4, 8>(st, d_desc, d_reals);
+    case 10: return launch<10, 4, 8>(st, d_desc, d_reals);
+    case 11: return launch<11, 4, 4>(st, d_desc, d_reals);
+    case 12: return launch<12, 4, 2>(st, d_desc, d_reals);
+    case 13: return launch<13, 4, 1>(st, d_desc, d_reals);
+    default:
+      snprintf(msg, sizeof msg, "TILE descriptor: tile size 2^%d is not built (9..13)", A);
+      set_error(msg);
+      return 1;
+  }
 }
 
 }  // namespace b200

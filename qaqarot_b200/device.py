@@ -147,3 +147,36 @@ class DeviceState:
 
     def sync(self) -> None:
         _lib.check(self._lib.b200_sync(self._h))
+
+    # -- timing (bench.py / profiling) ------------------------------------------------------------
+    def event_record(self, slot: int) -> None:
+        _lib.check(self._lib.b200_event_record(self._h, slot))
+
+    def event_elapsed_ms(self, slot_a: int, slot_b: int) -> float:
+        ms = C.c_double()
+        _lib.check(self._lib.b200_event_elapsed_ms(self._h, slot_a, slot_b, C.byref(ms)))
+        return ms.value
+
+
+class PinnedBuffer:
+    """Page-locked host memory exposed as a complex128 ndarray (destination of fast downloads)."""
+
+    def __init__(self, count: int):
+        self._lib = _lib.load()
+        self._p = C.c_void_p()
+        self.count = count
+        _lib.check(self._lib.b200_host_alloc(16 * max(1, count), C.byref(self._p)))
+        buf = (C.c_double * (2 * count)).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=np.complex128, count=count)
+
+    def close(self) -> None:
+        if getattr(self, "_p", None) is not None and self._p.value:
+            self.array = None
+            self._lib.b200_host_free(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

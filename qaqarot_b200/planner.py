@@ -1,6 +1,559 @@
-"""Fusion planner (placeholder: one pass per primitive until the tile pass lands)."""
-from .program import unfused_program
+"""Gate-fusion planner: primitives -> fused tile passes (the descriptors csrc/tile.cu executes).
+
+The reference applies one gate per full sweep of the state (numpy_backend.py:545-570); its only fusion
+precedent is the `1q_compaction` transpiler (backends/onequbitgate_transpiler.py:12-51).  Gate application is
+HBM-bound, so this planner trades sweeps for on-chip work in three steps:
+
+1. ``normalize``: chains of uncontrolled 1-qubit gates collapse into one 2x2 (as 1q_compaction does, but also
+   across commuting controls); every diagonal gate becomes a *phase* ``amp *= w where (index & mask) == mask``
+   (a diag(d0, d1) gate is d0 times a phase d1/d0; the scalars are collected into one global factor); phases on
+   one or two qubits sharing a qubit are merged into *fans* ``amp *= [bit j] * w0 * prod_k (bit k ? w_k : 1)``
+   -- the controlled-phase ladder of a QFT is one fan per target.
+2. ``schedule``: greedy list scheduling into *passes*.  A pass owns a set T of `a` physical index bits (the
+   lowest `c` bits always, for coalesced rows, plus chosen high bits); a CTA holds the 2^a amplitudes of one
+   tile in shared memory.  Non-diagonal targets must lie in T; controls and phases may sit on any bit (bits
+   outside T are constant per tile).  Inside a pass gates are grouped into *rounds*: in a round each thread
+   keeps 2^r amplitudes in registers (the round's r register bits) and applies the round's gates there.
+   Commutation rule: two gates may be reordered unless they share a qubit on which one is non-diagonal.
+3. ``encode``: the descriptor words / payload reals documented in csrc/tile.cu.
+
+Rounding differs from the gate-by-gate reference only by the re-association of products (~1e-16 per fused
+gate), far inside the 1e-12 parity budget.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, FrozenSet, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .lowering import Prim
+from .program import Program
+
+K_MAT, K_X, K_PHASE, K_FAN = 1, 2, 3, 4
+F_REAL = 1
+MAX_FANS = 64            # per pass (shared-memory slots in csrc/tile.cu)
 
 
-def plan(prims, n_qubits):
-    return unfused_program(prims)
+@dataclass
+class PlanConfig:
+    a: int = 12               # tile bits (2^a amplitudes of 16 B in shared memory)
+    r: int = 4                # register bits per round (2^r amplitudes per thread)
+    c: int = 4                # contiguous low bits always in the tile (2^c * 16 B rows)
+    max_rounds: int = 6
+    min_qubits: int = 9       # below this the state is tiny: one kernel per gate
+    max_cost: float = 150.0   # DFMA-equivalents per amplitude per pass before a new pass is opened
+    scan_limit: int = 4096    # how far ahead of the first unscheduled item a pass may look
+    kernel_tiles: Tuple[int, ...] = (9, 10, 11, 12, 13)   # tile sizes csrc/tile.cu instantiates (r = 4)
+
+
+DEFAULT = PlanConfig()
+
+
+class Item:
+    """One schedulable unit after normalisation."""
+    __slots__ = ("kind", "t", "ctrls", "m", "bits", "w", "entries", "aux", "nd", "dg", "n_prims", "pos")
+
+    def __init__(self, kind, t=-1, ctrls=(), m=None, bits=(), w=1.0 + 0j, entries=None, aux=-1, n_prims=1):
+        self.kind = kind            # mat | x | phase | fan | swap
+        self.t = t                  # mat/x: target; fan: target; swap: first qubit
+        self.ctrls = tuple(ctrls)   # mat/x
+        self.m = m                  # mat: 4 complex, row major
+        self.bits = tuple(bits)     # phase: qubits that must all be 1
+        self.w = complex(w)         # phase: factor; fan: w0
+        self.entries = entries      # fan: {qubit: factor}
+        self.aux = aux              # swap: second qubit
+        self.n_prims = n_prims
+        self.pos = -1
+        self.refresh()
+
+    def refresh(self):
+        if self.kind in ("mat", "x"):
+            self.nd = frozenset((self.t,))
+            self.dg = frozenset(self.ctrls)
+        elif self.kind == "swap":
+            self.nd = frozenset((self.t, self.aux))
+            self.dg = frozenset()
+        elif self.kind == "phase":
+            self.nd = frozenset()
+            self.dg = frozenset(self.bits)
+        else:
+            self.nd = frozenset()
+            self.dg = frozenset((self.t,) + tuple(self.entries))
+
+    def __repr__(self):
+        if self.kind == "fan":
+            return f"<fan t{self.t} {sorted(self.entries)}>"
+        if self.kind == "phase":
+            return f"<phase {list(self.bits)}>"
+        if self.kind == "swap":
+            return f"<swap {self.t},{self.aux}>"
+        return f"<{self.kind} t{self.t} c{list(self.ctrls)}>"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# 1. normalisation
+# ---------------------------------------------------------------------------------------------------------
+_ID = np.array([1, 0, 0, 1], dtype=complex)
+_XM = np.array([0, 1, 1, 0], dtype=complex)
+
+
+def _mul(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Row-major 2x2 product a @ b."""
+    return np.array([a[0] * b[0] + a[1] * b[2], a[0] * b[1] + a[1] * b[3],
+                     a[2] * b[0] + a[3] * b[2], a[2] * b[1] + a[3] * b[3]], dtype=complex)
+
+
+def _as_matrix(p: Prim) -> np.ndarray:
+    if p.kind == "mat":
+        return np.asarray(p.data, dtype=complex).reshape(4)
+    if p.kind == "diag":
+        return np.array([p.data[0], 0, 0, p.data[1]], dtype=complex)
+    return _XM
+
+
+class Normalized:
+    def __init__(self):
+        self.items: List[Item] = []
+        self.n_prims = 0
+
+
+def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = True) -> Normalized:
+    out = Normalized()
+    items = out.items
+    pending: List[Optional[np.ndarray]] = [None] * n
+    pending_count = [0] * n
+    scalar = [1.0 + 0j]
+    # Items carry a sortable key (major, minor).  Gates arriving in program order are appended (next major);
+    # a fused 1-qubit gate, emitted only when something forces it out, is *inserted* right after the last item
+    # touching its qubit -- it commutes with everything in between, and placing it early keeps later phases
+    # mergeable into the fans that precede it.
+    start = (-1, 0)
+    last_nd = [start] * n                # key of the last item that is non-diagonal on qubit q
+    last_touch = [start] * n             # key of the last item involving qubit q at all
+    open_fans: Dict[int, Item] = {}      # target qubit -> most recent fan with that target
+    counter = [0, 0]
+
+    def push(it: Item, after=None):
+        if after is None:
+            it.pos = (counter[0], 0)
+            counter[0] += 1
+        else:
+            counter[1] += 1
+            it.pos = (after[0], after[1] + counter[1])
+        items.append(it)
+        for q in it.nd:
+            last_nd[q] = max(last_nd[q], it.pos)
+        for q in it.nd | it.dg:
+            last_touch[q] = max(last_touch[q], it.pos)
+
+    def accepts(fan: Item, bits) -> bool:
+        return all(last_nd[b] < fan.pos for b in bits)
+
+    def touch(it: Item, bits):
+        for q in bits:
+            last_touch[q] = max(last_touch[q], it.pos)
+
+    def emit_phase(bits: Tuple[int, ...], w: complex, count: int, early: bool = False):
+        if w == 1.0:
+            return
+        if len(bits) == 0:
+            scalar[0] *= w
+            return
+        if fans and len(bits) == 1:
+            j = bits[0]
+            f = open_fans.get(j)
+            if f is not None and accepts(f, bits):
+                f.w *= w
+                f.n_prims += count
+                return
+            f = Item("fan", t=j, w=w, entries={}, n_prims=count)
+            push(f, last_touch[j] if early else None)
+            open_fans[j] = f
+            return
+        if fans and len(bits) == 2:
+            k, j = bits
+            for tgt, other in ((j, k), (k, j)):
+                f = open_fans.get(tgt)
+                if f is not None and accepts(f, bits):
+                    f.entries[other] = f.entries.get(other, 1.0 + 0j) * w
+                    f.n_prims += count
+                    f.refresh()
+                    touch(f, bits)
+                    return
+            f = Item("fan", t=j, w=1.0 + 0j, entries={k: complex(w)}, n_prims=count)
+            push(f)
+            open_fans[j] = f
+            return
+        push(Item("phase", bits=bits, w=w, n_prims=count))
+
+    def flush(q: int):
+        m, cnt = pending[q], pending_count[q]
+        pending[q], pending_count[q] = None, 0
+        if m is None:
+            return
+        if m[1] == 0 and m[2] == 0 and abs(m[0]) > 0.5:
+            if m[0] != 1.0:
+                scalar[0] *= m[0]
+                emit_phase((q,), m[3] / m[0], cnt, early=True)
+            else:
+                emit_phase((q,), m[3], cnt, early=True)
+            return
+        if np.array_equal(m, _XM):
+            push(Item("x", t=q, n_prims=cnt), last_touch[q])
+        else:
+            push(Item("mat", t=q, m=m, n_prims=cnt), last_touch[q])
+
+    for p in prims:
+        out.n_prims += 1
+        if p.kind == "swap":
+            a, b = p.target, p.aux
+            pending[a], pending[b] = pending[b], pending[a]
+            pending_count[a], pending_count[b] = pending_count[b], pending_count[a]
+            push(Item("swap", t=a, aux=b))
+            continue
+        if not p.controls and fuse_1q:
+            g = _as_matrix(p)
+            t = p.target
+            pending[t] = g if pending[t] is None else _mul(g, pending[t])
+            pending_count[t] += 1
+            continue
+        if not p.controls:
+            pending[p.target] = _as_matrix(p)
+            pending_count[p.target] = 1
+            flush(p.target)
+            continue
+        # controlled gate: a diagonal pending factor commutes with a control, anything else is flushed first
+        for cq in p.controls:
+            m = pending[cq]
+            if m is not None and not (m[1] == 0 and m[2] == 0):
+                flush(cq)
+        if p.kind == "diag":
+            m = pending[p.target]
+            if m is not None and not (m[1] == 0 and m[2] == 0):
+                flush(p.target)
+            d0, d1 = complex(p.data[0]), complex(p.data[1])
+            if d0 == 1.0:
+                emit_phase(p.controls + (p.target,), d1, 1)
+            elif abs(d0) > 0.5:
+                emit_phase(p.controls, d0, 1)
+                emit_phase(p.controls + (p.target,), d1 / d0, 0)
+            else:
+                flush(p.target)
+                push(Item("mat", t=p.target, ctrls=p.controls, m=np.array([d0, 0, 0, d1], dtype=complex)))
+            continue
+        flush(p.target)
+        if p.kind == "x":
+            push(Item("x", t=p.target, ctrls=p.controls))
+        else:
+            push(Item("mat", t=p.target, ctrls=p.controls, m=np.asarray(p.data, dtype=complex).reshape(4)))
+    for q in range(n):
+        flush(q)
+    if scalar[0] != 1.0:
+        push(Item("phase", bits=(), w=scalar[0], n_prims=0))
+    items.sort(key=lambda it: it.pos)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# 2. scheduling
+# ---------------------------------------------------------------------------------------------------------
+def _cost(it: Item) -> float:
+    """Rough DFMA-equivalents per amplitude."""
+    if it.kind == "mat":
+        base = 4.0 if np.all(np.asarray(it.m).imag == 0) else 8.0
+        return base / (1 << len(it.ctrls))
+    if it.kind == "x":
+        return 0.5
+    if it.kind == "phase":
+        return 4.0 / (1 << len(it.bits))
+    if it.kind == "fan":
+        return 5.0
+    return 0.0
+
+
+@dataclass
+class Round:
+    reg: List[int]                       # physical qubits held in registers (r of them)
+    items: List[Item] = field(default_factory=list)
+
+
+@dataclass
+class Pass:
+    tile: List[int]                      # physical tile bits, ascending (first c are 0..c-1)
+    rounds: List[Round] = field(default_factory=list)
+
+
+def _conflict(it: Item, skipped_nd: set, skipped_dg: set) -> bool:
+    for q in it.nd:
+        if q in skipped_nd or q in skipped_dg:
+            return True
+    for q in it.dg:
+        if q in skipped_nd:
+            return True
+    return False
+
+
+def build_pass(remaining: List[Item], n: int, a: int, r: int, c: int, cfg: PlanConfig) -> Tuple[Pass, List[Item]]:
+    """Greedy: returns the pass and the items left over (program order preserved)."""
+    tile = set(range(c))
+    rounds: List[Round] = []
+    done = [False] * len(remaining)
+    cost = 0.0
+    n_fans = 0
+    limit = min(len(remaining), cfg.scan_limit)
+    for _ in range(cfg.max_rounds):
+        reg: List[int] = []
+        picked: List[int] = []
+        skipped_nd: set = set()
+        skipped_dg: set = set()
+        for idx in range(limit):
+            if done[idx]:
+                continue
+            it = remaining[idx]
+            ok = it.kind != "swap" and not _conflict(it, skipped_nd, skipped_dg)
+            if ok and it.kind == "fan" and n_fans >= MAX_FANS - 1:
+                ok = False
+            if ok and it.nd:
+                t = it.t
+                new_t = t not in tile
+                new_r = t not in reg
+                if (new_t and len(tile) >= a) or (new_r and len(reg) >= r) or cost + _cost(it) > cfg.max_cost:
+                    ok = False
+                else:
+                    if new_t:
+                        tile.add(t)
+                    if new_r:
+                        reg.append(t)
+            if ok:
+                picked.append(idx)
+                cost += _cost(it)
+                n_fans += it.kind == "fan"
+            else:
+                skipped_nd |= it.nd
+                skipped_dg |= it.dg
+                if len(skipped_nd) >= n:
+                    break
+        if not picked:
+            break
+        if not reg and rounds:
+            # only phases / fans became ready: they need no register bits of their own, fold into the last round
+            rounds[-1].items += [remaining[i] for i in picked]
+        else:
+            rounds.append(Round(reg, [remaining[i] for i in picked]))
+        for i in picked:
+            done[i] = True
+    # complete the tile with the lowest unused bits, then every round's register set with unused tile bits
+    q = c
+    while len(tile) < a:
+        while q in tile:
+            q += 1
+        tile.add(q)
+    tl = sorted(tile)
+    for rd in rounds:
+        for q in reversed(tl):
+            if len(rd.reg) >= r:
+                break
+            if q not in rd.reg:
+                rd.reg.append(q)
+    return Pass(tl, rounds), [it for i, it in enumerate(remaining) if not done[i]]
+
+
+def _thread_order(tile: List[int], reg: List[int]) -> List[int]:
+    """Local bit indices: register bits first, then thread bits.  The three lowest thread bits are chosen with
+    distinct residues mod 3 when possible, which makes the XOR-swizzled 16-byte shared-memory accesses of a
+    quarter warp conflict free (csrc/tile.cu)."""
+    loc = {q: i for i, q in enumerate(tile)}
+    regl = [loc[q] for q in reg]
+    rest = [i for i in range(len(tile)) if i not in regl]
+    first: List[int] = []
+    for res in (0, 1, 2):
+        for i in rest:
+            if i % 3 == res and i not in first:
+                first.append(i)
+                break
+    first.sort()
+    rest = first + [i for i in rest if i not in first]
+    return regl + rest
+
+
+# ---------------------------------------------------------------------------------------------------------
+# 3. encoding
+# ---------------------------------------------------------------------------------------------------------
+def _pack8(vals: Sequence[int]) -> Tuple[int, int]:
+    v = list(vals) + [0] * (16 - len(vals))
+    lo = sum((x & 0xFF) << (8 * i) for i, x in enumerate(v[:8]))
+    hi = sum((x & 0xFF) << (8 * i) for i, x in enumerate(v[8:16]))
+    return lo, hi
+
+
+def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int) -> None:
+    a = len(ps.tile)
+    tile = ps.tile
+    loc = {q: i for i, q in enumerate(tile)}
+    nt = a - r
+    fan_records: List[List[int]] = []          # per fan: [n_entries | roff << 32, masks...]
+    round_words: List[int] = []
+    n_prims = 0
+
+    def split_mask(qubits, order) -> Tuple[int, int, int]:
+        """-> (thread-part local mask, register-part rho mask, fixed physical mask)"""
+        lm = rm = fm = 0
+        for q in qubits:
+            if q in loc:
+                li = loc[q]
+                k = order.index(li)
+                if k < r:
+                    rm |= 1 << k
+                else:
+                    lm |= 1 << li
+            else:
+                fm |= 1 << q
+        return lm, rm, fm
+
+    scalars: List[Tuple[int, complex]] = []     # (fixed-bit mask, factor): diagonal gates constant over a tile
+
+    def fan_gate(order, fid_entries, w0, lw, tgt) -> List[int]:
+        """Encode one fan: fixed (mask, w) entries, local per-bit factors `lw`, optional target qubit."""
+        fid = len(fan_records)
+        lm = fm = skip = 0
+        if tgt is not None:
+            if tgt in loc:
+                k = order.index(loc[tgt])
+                if k < r:
+                    skip = sum(1 << rho for rho in range(1 << r) if not (rho >> k) & 1)
+                else:
+                    lm = 1 << loc[tgt]
+            else:
+                fm = 1 << tgt
+        fr_off = prog.add_reals([w0] + [w for _, w in fid_entries])
+        fan_records.append([len(fid_entries) | (fr_off << 32)] + [m for m, _ in fid_entries])
+        tbits = order[r:]
+        lane_t = np.ones(32, dtype=complex)
+        for x in range(32):
+            for i in range(min(5, nt)):
+                if (x >> i) & 1 and tbits[i] in lw:
+                    lane_t[x] *= lw[tbits[i]]
+        warp_t = np.ones(1 << max(0, nt - 5), dtype=complex)
+        for y in range(warp_t.size):
+            for i in range(5, nt):
+                if (y >> (i - 5)) & 1 and tbits[i] in lw:
+                    warp_t[y] *= lw[tbits[i]]
+        reg_t = np.ones(1 << r, dtype=complex)
+        for rho in range(1 << r):
+            for i in range(r):
+                if (rho >> i) & 1 and order[i] in lw:
+                    reg_t[rho] *= lw[order[i]]
+        roff = prog.add_reals(list(lane_t) + list(warp_t) + list(reg_t))
+        return [K_FAN | (fid << 24) | (lm << 32) | (skip << 48), fm, roff]
+
+    encoded_rounds: List[Tuple[List[int], List[int]]] = []
+    for rd in ps.rounds:
+        order = _thread_order(tile, rd.reg)
+        gates: List[int] = []
+        for it in rd.items:
+            n_prims += it.n_prims
+            if it.kind in ("mat", "x"):
+                j = order.index(loc[it.t])
+                assert j < r, "non-diagonal target outside the round's register bits"
+                lm, rm, fm = split_mask(it.ctrls, order)
+                if it.kind == "mat":
+                    real = bool(np.all(np.asarray(it.m).imag == 0))
+                    roff = prog.add_reals(it.m)
+                    g0 = K_MAT | (j << 8) | ((F_REAL if real else 0) << 16) | (lm << 32) | (rm << 48)
+                else:
+                    roff = 0
+                    g0 = K_X | (j << 8) | (lm << 32) | (rm << 48)
+                gates += [g0, fm, roff]
+            elif it.kind == "phase":
+                if not any(q in loc for q in it.bits):
+                    scalars.append((sum(1 << q for q in it.bits), it.w))
+                    continue
+                lm, rm, fm = split_mask(it.bits, order)
+                roff = prog.add_reals([it.w])
+                gates += [K_PHASE | (lm << 32) | (rm << 48), fm, roff]
+            else:                                           # fan
+                if it.t not in loc and not any(q in loc for q in it.entries):
+                    scalars.append((1 << it.t, it.w))
+                    scalars += [((1 << it.t) | (1 << q), w) for q, w in it.entries.items()]
+                    continue
+                fixed = [(1 << q, w) for q, w in it.entries.items() if q not in loc]
+                lw = {loc[q]: w for q, w in it.entries.items() if q in loc}
+                gates += fan_gate(order, fixed, it.w, lw, it.t)
+        encoded_rounds.append((order, gates))
+    if scalars:
+        order, gates = encoded_rounds[-1]
+        gates += fan_gate(order, scalars, 1.0 + 0j, {}, None)
+    for order, gates in encoded_rounds:
+        o_lo, o_hi = _pack8(order)
+        round_words += [(len(gates) // 3) | ((3 + len(gates)) << 16), o_lo, o_hi] + gates
+    assert len(fan_records) <= MAX_FANS
+
+    t_lo, t_hi = _pack8(tile)
+    n_fans = len(fan_records)
+    directory: List[int] = []
+    body: List[int] = []
+    base = 4 + n_fans
+    for rec in fan_records:
+        directory.append(base + len(body))
+        body += rec
+    rounds_off = base + len(body)
+    words = [a | (c << 8) | (r << 16) | (len(ps.rounds) << 24) | (n_fans << 32), t_lo, t_hi,
+             4 | (rounds_off << 32)] + directory + body + round_words
+    woff = prog.add_words(words)
+    prog.add_op(_lib.OP_TILE, woff=woff, wlen=len(words), nbytes=32.0 * 2 ** n)
+    prog.n_prims += n_prims
+
+
+def _emit_single(prog: Program, it: Item, n: int) -> None:
+    """One item as its own kernel launch (tiny states, swaps, and the fusion-off mode)."""
+    dim = 2.0 ** n
+    if it.kind == "mat":
+        prog.add_op(_lib.OP_MAT, it.t, cmask=sum(1 << q for q in it.ctrls), roff=prog.add_reals(it.m),
+                    nbytes=32.0 * dim / (1 << len(it.ctrls)))
+    elif it.kind == "x":
+        prog.add_op(_lib.OP_X, it.t, cmask=sum(1 << q for q in it.ctrls), nbytes=32.0 * dim / (1 << len(it.ctrls)))
+    elif it.kind == "swap":
+        prog.add_op(_lib.OP_SWAP, it.t, aux=it.aux, nbytes=16.0 * dim)
+    elif it.kind == "phase":
+        if not it.bits:
+            prog.add_op(_lib.OP_SCALE, roff=prog.add_reals([it.w]), nbytes=32.0 * dim)
+        else:
+            prog.add_op(_lib.OP_DIAG, it.bits[-1], cmask=sum(1 << q for q in it.bits[:-1]),
+                        roff=prog.add_reals([1.0, it.w]), nbytes=32.0 * dim / (1 << len(it.bits)))
+    else:
+        if it.w != 1.0:
+            prog.add_op(_lib.OP_DIAG, it.t, roff=prog.add_reals([1.0, it.w]), nbytes=16.0 * dim)
+        for q, w in it.entries.items():
+            prog.add_op(_lib.OP_DIAG, it.t, cmask=1 << q, roff=prog.add_reals([1.0, w]), nbytes=8.0 * dim)
+    prog.n_prims += it.n_prims
+
+
+def plan(prims: Sequence[Prim], n_qubits: int, cfg: PlanConfig = DEFAULT) -> Program:
+    """Primitives of one unitary segment -> op program."""
+    n = n_qubits
+    prog = Program()
+    if not prims:
+        return prog
+    norm = normalize(prims, n)
+    if n < cfg.min_qubits:
+        for it in norm.items:
+            _emit_single(prog, it, n)
+        return prog
+    a = min(cfg.a, n)
+    if a not in cfg.kernel_tiles:
+        a = max(t for t in cfg.kernel_tiles if t <= a)
+    r = min(cfg.r, a)
+    c = min(cfg.c, a)
+    remaining = list(norm.items)
+    while remaining:
+        if remaining[0].kind == "swap":
+            _emit_single(prog, remaining.pop(0), n)
+            continue
+        ps, rest = build_pass(remaining, n, a, r, c, cfg)
+        if not ps.rounds:                                   # cannot happen: the head item always fits
+            raise RuntimeError(f"planner made no progress at {remaining[0]}")
+        encode_pass(prog, ps, n, r, c)
+        remaining = rest
+    return prog

@@ -20,6 +20,7 @@ class Program:
         self.n_passes = 0         # state passes (one per op)
         self.pass_bytes = 0.0     # algorithmic bytes moved, summed over passes (set by the planner)
         self._frozen = None
+        self._bytes: List[float] = []   # algorithmic bytes per op (read + write of the amplitudes it touches)
 
     # -- building -------------------------------------------------------------------------------
     def add_reals(self, values: Sequence[complex]) -> int:
@@ -35,24 +36,32 @@ class Program:
         return off
 
     def add_op(self, kind: int, target: int = 0, aux: int = 0, cmask: int = 0, roff: int = 0, woff: int = 0,
-               wlen: int = 0) -> None:
+               wlen: int = 0, nbytes: float = 0.0) -> None:
         self._ops.append((kind, target, aux, wlen, cmask, woff, roff))
+        self._bytes.append(float(nbytes))
         self.n_passes += 1
+        self.pass_bytes += float(nbytes)
         self._frozen = None
 
-    def add_prim(self, p: Prim) -> None:
+    @property
+    def op_bytes(self) -> List[float]:
+        return self._bytes
+
+    def add_prim(self, p: Prim, n_qubits: int = 0) -> None:
         """One primitive as its own single-gate pass."""
         cmask = 0
         for c in p.controls:
             cmask |= 1 << c
+        full = 32.0 * 2.0 ** n_qubits / (1 << len(p.controls))
         if p.kind == "mat":
-            self.add_op(_lib.OP_MAT, p.target, cmask=cmask, roff=self.add_reals(p.data))
+            self.add_op(_lib.OP_MAT, p.target, cmask=cmask, roff=self.add_reals(p.data), nbytes=full)
         elif p.kind == "diag":
-            self.add_op(_lib.OP_DIAG, p.target, cmask=cmask, roff=self.add_reals(p.data))
+            touched = full / 2 if complex(p.data[0]) == 1.0 else full
+            self.add_op(_lib.OP_DIAG, p.target, cmask=cmask, roff=self.add_reals(p.data), nbytes=touched)
         elif p.kind == "x":
-            self.add_op(_lib.OP_X, p.target, cmask=cmask)
+            self.add_op(_lib.OP_X, p.target, cmask=cmask, nbytes=full)
         elif p.kind == "swap":
-            self.add_op(_lib.OP_SWAP, p.target, aux=p.aux)
+            self.add_op(_lib.OP_SWAP, p.target, aux=p.aux, nbytes=full / 2)
         else:
             raise ValueError(f"primitive {p.kind} is not a unitary pass")
         self.n_prims += 1
@@ -73,8 +82,8 @@ class Program:
         return len(self._ops)
 
 
-def unfused_program(prims: Sequence[Prim]) -> Program:
+def unfused_program(prims: Sequence[Prim], n_qubits: int = 0) -> Program:
     prog = Program()
     for p in prims:
-        prog.add_prim(p)
+        prog.add_prim(p, n_qubits)
     return prog
