@@ -198,7 +198,11 @@ def run_b200(args):
 
     n = args.qubits
     circ, wl = build_workload(args.workload, n, args.depth)
-    be = B200Backend(device=0, fusion=not args.no_fusion)
+    cfg = None
+    if args.tile_bits:
+        from qaqarot_b200.planner import PlanConfig
+        cfg = PlanConfig(a=args.tile_bits)
+    be = B200Backend(device=0, fusion=not args.no_fusion, plan_config=cfg)
     comp = be._compile(circ.ops, n, 0)
     prog = comp.prefix
     st = be._state(n)
@@ -245,7 +249,8 @@ def run_b200(args):
     cnt, tot = by_kind[dom]
     kind_names = {1: "k_mat", 2: "k_diag/k_phase", 3: "k_x", 4: "k_swapbits", 16: "k_tile", 17: "k_scale"}
     avg_ms = tot / cnt
-    alg_bytes = float(getattr(prog, "kind_bytes", {}).get(dom, pass_bytes))
+    dom_bytes = [b for b, o in zip(prog.op_bytes, prog._ops) if o[0] == dom]
+    alg_bytes = float(np.mean(dom_bytes)) if dom_bytes else pass_bytes
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -259,7 +264,11 @@ def run_b200(args):
                 "traffic": traffic, "kernel": kind_names.get(dom, str(dom)), "launches_timed": cnt,
                 "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "share_of_step": tot / total_ms}
-    hbm_gbs = prog.n_passes * pass_bytes / sec_per_step / 1e9
+    hbm_gbs = prog.pass_bytes / sec_per_step / 1e9
+    if args.detail:
+        with open(args.detail, "w") as f:
+            json.dump({"kinds": [int(k) for k in op_ms[-1][1]], "ms": [[float(x) for x in ms] for ms, _ in op_ms],
+                       "bytes": prog.op_bytes}, f)
 
     # end to end through the plugin API with host buffers
     pinned = PinnedBuffer(1 << n)
@@ -312,6 +321,8 @@ def main():
     ap.add_argument("--qubits", type=int, default=30)
     ap.add_argument("--depth", type=int, default=20)
     ap.add_argument("--no-fusion", action="store_true")
+    ap.add_argument("--tile-bits", type=int, default=0, help="override the planner's tile size (log2 amplitudes)")
+    ap.add_argument("--detail", default="", help="write per-op device times of the timed steps to this JSON file")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
     args = ap.parse_args()

@@ -38,6 +38,9 @@ enum {
   B200_OP_X     = 3,  /* pair swap on `target` under `cmask` (x / cx / ccx as pure permutations)          */
   B200_OP_SWAP  = 4,  /* exchange qubits `target` and `aux` (swap gate; reference falls back to 3 cx,
                          gate.py:1172-1177)                                                                */
+  B200_OP_PERMUTE = 5, /* in-place involution of index bits: `woff/wlen` locate wlen words p | q << 8, disjoint
+                         transpositions (p, q).  The planner relabels swap gates and emits at most two of
+                         these at the end of a program instead of 3 CX sweeps per swap (gate.py:1172-1177)   */
   B200_OP_TILE  = 16, /* fused tile-resident pass: `woff/wlen` locate its descriptor in `words`            */
   B200_OP_SCALE = 17  /* multiply the whole state by reals[0..1]                                           */
 };
@@ -46,7 +49,7 @@ typedef struct b200_op {
   int32_t  kind;    /* B200_OP_*                                            */
   int32_t  target;  /* target qubit                                         */
   int32_t  aux;     /* second qubit (SWAP)                                  */
-  int32_t  wlen;    /* TILE: descriptor length in 64-bit words              */
+  int32_t  wlen;    /* TILE / PERMUTE: descriptor length in 64-bit words    */
   uint64_t cmask;   /* control mask over qubit indices (0 = uncontrolled)   */
   uint64_t woff;    /* TILE: descriptor offset into `words`                 */
   uint64_t roff;    /* offset of this op's payload in `reals` (doubles)     */

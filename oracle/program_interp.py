@@ -15,7 +15,7 @@ import numpy as np
 
 from oracle.sv_oracle import sub
 
-OP_MAT, OP_DIAG, OP_X, OP_SWAP, OP_TILE, OP_SCALE = 1, 2, 3, 4, 16, 17
+OP_MAT, OP_DIAG, OP_X, OP_SWAP, OP_PERMUTE, OP_TILE, OP_SCALE = 1, 2, 3, 4, 5, 16, 17
 
 
 def _bits(mask: int):
@@ -94,6 +94,16 @@ class OracleState:
                 t = a.copy()
                 a[...] = b
                 b[...] = t
+            elif o.kind == OP_PERMUTE:
+                pairs = [(int(w) & 0xFF, (int(w) >> 8) & 0xFF) for w in words[o.woff:o.woff + o.wlen]]
+                seen = [q for pq in pairs for q in pq]
+                assert len(set(seen)) == len(seen) and all(q < n for q in seen), "transpositions must be disjoint"
+                idx = np.arange(self.psi.size, dtype=np.int64)
+                src = idx.copy()
+                for p_, q_ in pairs:
+                    diff = ((src >> p_) ^ (src >> q_)) & 1
+                    src ^= (diff << p_) | (diff << q_)
+                self.psi[:] = self.psi[src]
             elif o.kind == OP_SCALE:
                 self.psi *= complex(reals[o.roff], reals[o.roff + 1])
             elif o.kind == OP_TILE:

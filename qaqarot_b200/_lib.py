@@ -14,7 +14,7 @@ from typing import List, Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libb200sv.so")
-SOURCES = ["b200sv.cu", "sample.cu", "tile.cu"]
+SOURCES = ["b200sv.cu", "sample.cu", "tile.cu", "permute.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -33,7 +33,7 @@ class Op(C.Structure):
                 ("cmask", C.c_uint64), ("woff", C.c_uint64), ("roff", C.c_uint64)]
 
 
-OP_MAT, OP_DIAG, OP_X, OP_SWAP, OP_TILE, OP_SCALE = 1, 2, 3, 4, 16, 17
+OP_MAT, OP_DIAG, OP_X, OP_SWAP, OP_PERMUTE, OP_TILE, OP_SCALE = 1, 2, 3, 4, 5, 16, 17
 
 _lib: Optional[C.CDLL] = None
 

@@ -1,0 +1,139 @@
+// permute.cu -- in-place index-bit involution (B200_OP_PERMUTE), sm_100a.
+//
+// The planner treats `swap` gates (which the reference expands to three CX sweeps, gate.py:1172-1177) as a
+// relabelling of which index bit a qubit lives on, and owes the state one physical bit permutation at the end
+// of a program (a QFT's final bit reversal is the textbook case).  Any permutation is the product of at most
+// two involutions, and an involution of index bits -- a set of disjoint transpositions (p_i, q_i) -- is applied
+// here in ONE pass over the state (32 * 2^n bytes, every amplitude read once and written once):
+//
+//   tile bits T = the low k bits (so rows of 2^k * 16 B stay contiguous in HBM) + the partners of those that
+//   are transposed + enough further low bits to fill a 2^A tile; transpositions inside T are done through
+//   shared memory (XOR-swizzled slots, as in tile.cu); transpositions entirely outside T pair tile t with
+//   tile t' (the tile number with those bit pairs exchanged): a CTA loads both tiles and writes each one,
+//   permuted, to the other's location.  Tiles with t' < t are left to their partner; tiles that map to
+//   themselves under an identity inner permutation are skipped without touching memory.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+namespace b200 {
+
+constexpr int kInvMaxA = 10;       // tile of up to 2^10 amplitudes (16 KiB), two tiles per CTA
+constexpr int kInvThreads = 256;
+
+struct InvDesc {
+  int a;                      // tile bits
+  int n_outer;                // transpositions between non-tile bits
+  unsigned char tile[kInvMaxA];        // physical positions, ascending
+  unsigned char src_local[kInvMaxA];   // destination local bit i takes source local bit src_local[i]
+  unsigned char ou[32], ov[32];        // outer pairs as bit positions of the (compressed) tile number
+  int inner_identity;
+};
+
+__device__ __forceinline__ uint32_t inv_swz(uint32_t l) {
+  return l ^ ((l >> 3) & 7u) ^ ((l >> 6) & 7u) ^ ((l >> 9) & 7u);
+}
+
+__global__ void __launch_bounds__(kInvThreads) k_involution(c128* __restrict__ amp, uint64_t n_tiles, InvDesc d) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  c128* sa = reinterpret_cast<c128*>(smem_raw);
+  c128* sb = sa + (1u << d.a);
+  const uint32_t n_local = 1u << d.a;
+  for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    uint64_t t2 = t;
+    for (int i = 0; i < d.n_outer; ++i) {
+      const uint64_t bu = (t >> d.ou[i]) & 1ull, bv = (t >> d.ov[i]) & 1ull;
+      if (bu != bv) t2 ^= (1ull << d.ou[i]) | (1ull << d.ov[i]);
+    }
+    if (t2 < t || (t2 == t && d.inner_identity)) continue;         // CTA-uniform
+    uint64_t base = t, base2 = t2;
+    for (int i = 0; i < d.a; ++i) {
+      base = insert_zero(base, d.tile[i]);
+      base2 = insert_zero(base2, d.tile[i]);
+    }
+    const bool two = t2 != t;
+    for (uint32_t l = threadIdx.x; l < n_local; l += kInvThreads) {
+      uint64_t off = 0;
+      for (int i = 0; i < d.a; ++i) off |= (uint64_t)((l >> i) & 1u) << d.tile[i];
+      const uint32_t s = inv_swz(l);
+      sa[s] = amp[base + off];
+      if (two) sb[s] = amp[base2 + off];
+    }
+    __syncthreads();
+    for (uint32_t l = threadIdx.x; l < n_local; l += kInvThreads) {
+      uint64_t off = 0;
+      uint32_t ls = 0;
+      for (int i = 0; i < d.a; ++i) {
+        off |= (uint64_t)((l >> i) & 1u) << d.tile[i];
+        ls |= ((l >> i) & 1u) << d.src_local[i];          // involution: source bit <-> destination bit
+      }
+      const uint32_t s = inv_swz(ls);
+      amp[base2 + off] = sa[s];
+      if (two) amp[base + off] = sb[s];
+    }
+    __syncthreads();
+  }
+}
+
+// pairs[i] = p | q << 8: disjoint transpositions of index bits.
+int launch_permute(b200_state* st, const uint64_t* pairs, int n_pairs) {
+  const int n = st->n;
+  int partner[64];
+  for (int i = 0; i < 64; ++i) partner[i] = i;
+  for (int i = 0; i < n_pairs; ++i) {
+    const int p = (int)(pairs[i] & 0xFF), q = (int)((pairs[i] >> 8) & 0xFF);
+    if (p >= n || q >= n || p == q || partner[p] != p || partner[q] != q) {
+      set_error("PERMUTE: transpositions must be disjoint pairs of distinct qubits below n_qubits");
+      return 1;
+    }
+    partner[p] = q;
+    partner[q] = p;
+  }
+  // tile: low k bits, their partners, then further low bits (with partners) while it fits
+  const int k = std::min(4, n);
+  bool in_tile[64] = {};
+  int count = 0;
+  auto add = [&](int b) { if (!in_tile[b]) { in_tile[b] = true; ++count; } };
+  for (int b = 0; b < k; ++b) { add(b); add(partner[b]); }
+  for (int b = k; b < n && count < kInvMaxA; ++b) {
+    if (in_tile[b]) continue;
+    const int need = partner[b] == b || in_tile[partner[b]] ? 1 : 2;
+    if (count + need > kInvMaxA) continue;
+    add(b);
+    add(partner[b]);
+  }
+  InvDesc d;
+  memset(&d, 0, sizeof d);
+  d.a = count;
+  int loc[64];
+  for (int b = 0, i = 0; b < n; ++b)
+    if (in_tile[b]) { d.tile[i] = (unsigned char)b; loc[b] = i++; }
+  d.inner_identity = 1;
+  for (int i = 0; i < d.a; ++i) {
+    d.src_local[i] = (unsigned char)loc[partner[d.tile[i]]];
+    if (d.src_local[i] != i) d.inner_identity = 0;
+  }
+  // outer pairs in tile-number coordinates (non-tile bits, compressed ascending)
+  int comp[64], c = 0;
+  for (int b = 0; b < n; ++b) comp[b] = in_tile[b] ? -1 : c++;
+  for (int b = 0; b < n; ++b)
+    if (!in_tile[b] && partner[b] > b) {
+      if (d.n_outer == 32) { set_error("PERMUTE: too many transpositions"); return 1; }
+      d.ou[d.n_outer] = (unsigned char)comp[b];
+      d.ov[d.n_outer] = (unsigned char)comp[partner[b]];
+      ++d.n_outer;
+    }
+  if (d.n_outer == 0 && d.inner_identity) return 0;
+  const uint64_t n_tiles = st->dim >> d.a;
+  const size_t smem = sizeof(c128) * 2 * (size_t(1) << d.a);
+  const uint64_t cap = (uint64_t)kSMs * 16;
+  const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, cap);
+  k_involution<<<grid, kInvThreads, smem, st->stream>>>(st->amp, n_tiles, d);
+  st->launches++;
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b200

@@ -29,7 +29,8 @@
 //     MAT  (1): 2x2 (reals[roff..+8), row major re/im) on register bit j where all masks are satisfied
 //     X    (2): pair swap on register bit j under the masks
 //     PHASE(3): amp *= reals[roff] where all masks are satisfied
-//     FAN  (4): amp *= fix[fan] * lane_t[lane] * warp_t[warp] * reg_t[rho] unless bit rho of reg_mask is set
+//     FAN  (4): amp *= fix[fan] * lane_t[lane] * warp_t[warp] * reg_t[rho] where register bit j of rho is set
+//               (j = R: every rho; reg_mask repeats this as a skip mask over rho for the interpreter)
 //               (tables at roff: 32 + 2^(A-R-5) + 2^R complex); thread_mask / fixed mask select the fan target
 #include "common.cuh"
 
@@ -51,6 +52,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
 }
+// Pull `bytes` (multiple of 16) starting at a 16-byte aligned global address into L2 (no SM-side destination).
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
@@ -60,62 +65,149 @@ __device__ __forceinline__ int byte_of(uint64_t lo, uint64_t hi, int i) {
 }
 
 // ---- register-resident gate bodies (J = register bit, compile time) ---------------------------------------
-template <int R, int J>
-__device__ __forceinline__ void mat_c(c128 (&v)[1 << R], const double* __restrict__ m, uint32_t rm) {
-  const c128 m00 = make_double2(m[0], m[1]), m01 = make_double2(m[2], m[3]);
-  const c128 m10 = make_double2(m[4], m[5]), m11 = make_double2(m[6], m[7]);
+// The pair / amplitude updates are written as inline PTX that reads and writes the *same* registers ("+d").
+// Plain C++ makes NVVM emit each result into a fresh virtual register; at the join after every gate the whole
+// 2^R-amplitude register tile is then copied back (64 moves per gate at R = 4 -- as many instructions as the
+// arithmetic itself, seen as IMAD.MOV in the first ncu source view).  In-place PTX leaves nothing to copy.
+
+// (a0, a1) <- (m00 a0 + m01 a1, m10 a0 + m11 a1), complex coefficients m = (re, im) as m[0..8)
+__device__ __forceinline__ void pair_mat_c(c128& a0, c128& a1, const double (&m)[8], const double (&nm)[4]) {
+  asm("{\n\t.reg .f64 t0, t1, t2, t3;\n\t"
+      "mul.f64 t0, %4, %0;\n\t"            // m00r a0x
+      "mul.f64 t1, %4, %1;\n\t"            // m00r a0y
+      "mul.f64 t2, %8, %0;\n\t"            // m10r a0x
+      "mul.f64 t3, %8, %1;\n\t"            // m10r a0y
+      "fma.rn.f64 t0, %12, %1, t0;\n\t"    // - m00i a0y
+      "fma.rn.f64 t1, %5, %0, t1;\n\t"     // + m00i a0x
+      "fma.rn.f64 t2, %14, %1, t2;\n\t"    // - m10i a0y
+      "fma.rn.f64 t3, %9, %0, t3;\n\t"     // + m10i a0x
+      "fma.rn.f64 t0, %6, %2, t0;\n\t"     // + m01r a1x
+      "fma.rn.f64 t1, %6, %3, t1;\n\t"     // + m01r a1y
+      "fma.rn.f64 t2, %10, %2, t2;\n\t"    // + m11r a1x
+      "fma.rn.f64 t3, %10, %3, t3;\n\t"    // + m11r a1y
+      "fma.rn.f64 %0, %13, %3, t0;\n\t"    // - m01i a1y
+      "fma.rn.f64 %1, %7, %2, t1;\n\t"     // + m01i a1x
+      "fma.rn.f64 t2, %15, %3, t2;\n\t"    // - m11i a1y
+      "fma.rn.f64 %3, %11, %2, t3;\n\t"    // + m11i a1x
+      "mov.f64 %2, t2;\n\t}"
+      : "+d"(a0.x), "+d"(a0.y), "+d"(a1.x), "+d"(a1.y)
+      : "d"(m[0]), "d"(m[1]), "d"(m[2]), "d"(m[3]), "d"(m[4]), "d"(m[5]), "d"(m[6]), "d"(m[7]),
+        "d"(nm[0]), "d"(nm[1]), "d"(nm[2]), "d"(nm[3]));
+}
+// same with real coefficients
+__device__ __forceinline__ void pair_mat_r(c128& a0, c128& a1, double m00, double m01, double m10, double m11) {
+  asm("{\n\t.reg .f64 t0, t1, t2, t3;\n\t"
+      "mul.f64 t0, %4, %0;\n\t"
+      "mul.f64 t1, %4, %1;\n\t"
+      "mul.f64 t2, %6, %0;\n\t"
+      "mul.f64 t3, %6, %1;\n\t"
+      "fma.rn.f64 %0, %5, %2, t0;\n\t"
+      "fma.rn.f64 %1, %5, %3, t1;\n\t"
+      "fma.rn.f64 %2, %7, %2, t2;\n\t"
+      "fma.rn.f64 %3, %7, %3, t3;\n\t}"
+      : "+d"(a0.x), "+d"(a0.y), "+d"(a1.x), "+d"(a1.y)
+      : "d"(m00), "d"(m01), "d"(m10), "d"(m11));
+}
+// a <- a * f   (nfy = -f.y)
+__device__ __forceinline__ void amp_mul(c128& a, double fx, double fy, double nfy) {
+  asm("{\n\t.reg .f64 t0, t1;\n\t"
+      "mul.f64 t0, %0, %2;\n\t"
+      "mul.f64 t1, %1, %2;\n\t"
+      "fma.rn.f64 t0, %1, %4, t0;\n\t"
+      "fma.rn.f64 %1, %0, %3, t1;\n\t"
+      "mov.f64 %0, t0;\n\t}"
+      : "+d"(a.x), "+d"(a.y)
+      : "d"(fx), "d"(fy), "d"(nfy));
+}
+
+// a0 <-> a1.  Also opaque in-place PTX: a C++ swap is a renaming in SSA form, and the register permutation it
+// leaves at the join defeated the copy coalescing of the *whole* tile (2030 -> 491 moves without it).
+__device__ __forceinline__ void pair_swap(c128& a0, c128& a1) {
+  asm("{\n\t.reg .f64 t0, t1;\n\t"
+      "mov.f64 t0, %0;\n\tmov.f64 t1, %1;\n\tmov.f64 %0, %2;\n\tmov.f64 %1, %3;\n\t"
+      "mov.f64 %2, t0;\n\tmov.f64 %3, t1;\n\t}"
+      : "+d"(a0.x), "+d"(a0.y), "+d"(a1.x), "+d"(a1.y));
+}
+
+// COND = false: no control among the register bits (the common case) -- straight-line code, no predicates.
+template <int R, int J, bool COND>
+__device__ __forceinline__ void mat_c(c128 (&v)[1 << R], const double* __restrict__ mp, uint32_t rm) {
+  double m[8], nm[4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = mp[i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) nm[i] = -m[2 * i + 1];
 #pragma unroll
   for (int rho = 0; rho < (1 << R); ++rho) {
     if (rho & (1 << J)) continue;
-    if ((rho & rm) == rm) {
-      const c128 a0 = v[rho], a1 = v[rho | (1 << J)];
-      v[rho] = cfma(m01, a1, cmul(m00, a0));
-      v[rho | (1 << J)] = cfma(m11, a1, cmul(m10, a0));
-    }
+    if (!COND || (rho & rm) == rm) pair_mat_c(v[rho], v[rho | (1 << J)], m, nm);
   }
 }
-template <int R, int J>
+template <int R, int J, bool COND>
 __device__ __forceinline__ void mat_r(c128 (&v)[1 << R], const double* __restrict__ m, uint32_t rm) {
   const double m00 = m[0], m01 = m[2], m10 = m[4], m11 = m[6];
 #pragma unroll
   for (int rho = 0; rho < (1 << R); ++rho) {
     if (rho & (1 << J)) continue;
-    if ((rho & rm) == rm) {
-      const c128 a0 = v[rho], a1 = v[rho | (1 << J)];
-      v[rho] = make_double2(fma(m01, a1.x, m00 * a0.x), fma(m01, a1.y, m00 * a0.y));
-      v[rho | (1 << J)] = make_double2(fma(m11, a1.x, m10 * a0.x), fma(m11, a1.y, m10 * a0.y));
-    }
+    if (!COND || (rho & rm) == rm) pair_mat_r(v[rho], v[rho | (1 << J)], m00, m01, m10, m11);
   }
 }
-template <int R, int J>
+template <int R, int J, bool COND>
 __device__ __forceinline__ void perm_x(c128 (&v)[1 << R], uint32_t rm) {
 #pragma unroll
   for (int rho = 0; rho < (1 << R); ++rho) {
     if (rho & (1 << J)) continue;
-    if ((rho & rm) == rm) {
-      const c128 a0 = v[rho];
-      v[rho] = v[rho | (1 << J)];
-      v[rho | (1 << J)] = a0;
-    }
+    if (!COND || (rho & rm) == rm) pair_swap(v[rho], v[rho | (1 << J)]);
   }
+}
+
+// One target gate on register bit J if it is the runtime target j.  Written as a chain of independent
+// `if (j == J)` blocks updating v in place (not a switch): every join then merges a value with itself, so the
+// register allocator keeps the 2^R amplitudes in place instead of shuffling them at the end of each case.
+template <int R, int J>
+__device__ __forceinline__ void apply_if(c128 (&v)[1 << R], int kind, bool real, int j, const double* m,
+                                         uint32_t rm) {
+  if (j != J) return;
+#ifndef EXP_NO_COND
+  if (rm == 0) {
+#endif
+#ifndef EXP_NO_PERMX
+    if (kind == K_X) perm_x<R, J, false>(v, 0);
+    else
+#endif
+#ifndef EXP_NO_MATC
+    if (real) mat_r<R, J, false>(v, m, 0);
+    else mat_c<R, J, false>(v, m, 0);
+#else
+    mat_r<R, J, false>(v, m, 0);
+#endif
+#ifndef EXP_NO_COND
+  } else {
+    if (kind == K_X) perm_x<R, J, true>(v, rm);
+    else if (real) mat_r<R, J, true>(v, m, rm);
+    else mat_c<R, J, true>(v, m, rm);
+  }
+#endif
 }
 
 template <int R>
 __device__ __forceinline__ void apply_target(c128 (&v)[1 << R], int kind, bool real, int j, const double* m,
                                              uint32_t rm) {
-#define B200_CASE(J)                                            \
-  case J:                                                       \
-    if (J < R) {                                                \
-      if (kind == K_X) perm_x<R, (J < R ? J : 0)>(v, rm);       \
-      else if (real) mat_r<R, (J < R ? J : 0)>(v, m, rm);       \
-      else mat_c<R, (J < R ? J : 0)>(v, m, rm);                 \
-    }                                                           \
-    break;
-  switch (j) {
-    B200_CASE(0) B200_CASE(1) B200_CASE(2) B200_CASE(3) B200_CASE(4)
-    default: break;
+  apply_if<R, 0>(v, kind, real, j, m, rm);
+  if (R > 1) apply_if<R, (R > 1 ? 1 : 0)>(v, kind, real, j, m, rm);
+  if (R > 2) apply_if<R, (R > 2 ? 2 : 0)>(v, kind, real, j, m, rm);
+  if (R > 3) apply_if<R, (R > 3 ? 3 : 0)>(v, kind, real, j, m, rm);
+}
+
+// Fan on the amplitudes whose register bit K is set (K = R: every amplitude).
+template <int R, int K>
+__device__ __forceinline__ void fan_apply(c128 (&v)[1 << R], c128 wt, const double2* __restrict__ reg_t) {
+#pragma unroll
+  for (int rho = 0; rho < (1 << R); ++rho) {
+    if (K < R && !((rho >> K) & 1)) continue;
+    const c128 f = cmul(wt, reg_t[rho]);
+    amp_mul(v[rho], f.x, f.y, -f.y);
   }
-#undef B200_CASE
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------------
@@ -138,10 +230,10 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
   uint64_t off_t = 0;
 #pragma unroll
   for (int b = 0; b < NTB; ++b) off_t |= (uint64_t)((tid >> b) & 1u) << byte_of(tb_lo, tb_hi, b);
-  uint64_t hb[R];
-#pragma unroll
-  for (int k = 0; k < R; ++k) hb[k] = 1ull << byte_of(tb_lo, tb_hi, NTB + k);
   const uint32_t sw_t = swz(tid);
+  // rows of 2^c contiguous amplitudes; this thread prefetches rows tid, tid + NT, ... of the *next* tile into L2
+  const int c_bits = (int)((h0 >> 8) & 0xFF);
+  const uint32_t n_rows = 1u << (A - c_bits), row_bytes = 16u << c_bits;
 
   for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     uint64_t base = tile;
@@ -149,14 +241,29 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
     for (int i = 0; i < A; ++i) base = insert_zero(base, byte_of(tb_lo, tb_hi, i));
     const uint64_t fixedidx = base | index_offset;
     c128* __restrict__ g = amp + base + off_t;
+    if (tile + gridDim.x < n_tiles) {
+      uint64_t nbase = tile + gridDim.x;
+#pragma unroll
+      for (int i = 0; i < A; ++i) nbase = insert_zero(nbase, byte_of(tb_lo, tb_hi, i));
+      for (uint32_t row = tid; row < n_rows; row += NT) {
+        uint64_t roff = 0;
+        for (int b = c_bits; b < A; ++b) roff |= (uint64_t)((row >> (b - c_bits)) & 1u) << byte_of(tb_lo, tb_hi, b);
+        prefetch_l2_bulk(amp + nbase + roff, row_bytes);
+      }
+    }
 
+    {
+      uint64_t hb[R];
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
-      uint64_t off = 0;
+      for (int k = 0; k < R; ++k) hb[k] = 1ull << byte_of(tb_lo, tb_hi, NTB + k);
 #pragma unroll
-      for (int k = 0; k < R; ++k)
-        if ((i >> k) & 1) off |= hb[k];
-      cp_async16(&sm[sw_t ^ swz_c((uint32_t)i * NT)], g + off);
+      for (int i = 0; i < PER; ++i) {
+        uint64_t off = 0;
+#pragma unroll
+        for (int k = 0; k < R; ++k)
+          if ((i >> k) & 1) off |= hb[k];
+        cp_async16(&sm[sw_t ^ swz_c((uint32_t)i * NT)], g + off);
+      }
     }
 
     // per-tile fixed-bit products of the fans, while the copies are in flight (one warp per fan)
@@ -204,49 +311,72 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
         v[rho] = sm[s];
       }
 
+      // One structured body per gate, no `continue`: with early exits ptxas split the live ranges of the whole
+      // register tile at the loop head and copied all 2^R amplitudes twice per gate.
       const uint64_t* __restrict__ gp = rp + 3;
       for (int gi = 0; gi < ng; ++gi, gp += 3) {
         const uint64_t g0 = gp[0], fm = gp[1];
-        if ((fixedidx & fm) != fm) continue;                       // CTA-uniform
-        const double* __restrict__ pay = reals + gp[2];
-        const int kind = (int)(g0 & 0xFF);
         const uint32_t lm = (uint32_t)((g0 >> 32) & 0xFFFF), rm = (uint32_t)((g0 >> 48) & 0xFFFF);
-        if ((lt & lm) != lm) continue;                             // per thread
-        if (kind == K_MAT || kind == K_X) {
-          apply_target<R>(v, kind, ((g0 >> 16) & 1) != 0, (int)((g0 >> 8) & 0xFF), pay, rm);
-        } else if (kind == K_PHASE) {
-          const c128 w = make_double2(pay[0], pay[1]);
+        // fixed-bit condition: CTA-uniform; thread-bit condition: per thread
+        const bool active = ((fixedidx & fm) == fm) && ((lt & lm) == lm);
+        if (active) {
+          const double* __restrict__ pay = reals + gp[2];
+          const int kind = (int)(g0 & 0xFF), j = (int)((g0 >> 8) & 0xFF);
+          if (kind == K_MAT || kind == K_X) apply_target<R>(v, kind, ((g0 >> 16) & 1) != 0, j, pay, rm);
+#ifndef EXP_NO_PHASE
+          if (kind == K_PHASE) {
+            const double wx = pay[0], wy = pay[1];
 #pragma unroll
-          for (int rho = 0; rho < PER; ++rho)
-            if ((rho & rm) == rm) v[rho] = cmul(v[rho], w);
-        } else if (kind == K_FAN) {
-          const double2* __restrict__ tab = reinterpret_cast<const double2*>(pay);
-          const c128 wt = cmul(fix[(g0 >> 24) & 0xFF], cmul(tab[lane], tab[32 + (NWARP_T > 1 ? warp : 0)]));
-#pragma unroll
-          for (int rho = 0; rho < PER; ++rho)
-            if (!((rm >> rho) & 1u)) v[rho] = cmul(v[rho], cmul(wt, tab[32 + NWARP_T + rho]));
+            for (int rho = 0; rho < PER; ++rho)
+              if ((rho & rm) == rm) amp_mul(v[rho], wx, wy, -wy);
+          }
+#endif
+#ifndef EXP_NO_FAN
+          if (kind == K_FAN) {
+            const double2* __restrict__ tab = reinterpret_cast<const double2*>(pay);
+            const c128 wt = cmul(fix[(g0 >> 24) & 0xFF], cmul(tab[lane], tab[32 + (NWARP_T > 1 ? warp : 0)]));
+            const double2* __restrict__ reg_t = tab + 32 + NWARP_T;
+            if (j == 0) fan_apply<R, 0>(v, wt, reg_t);
+            if (j == 1) fan_apply<R, (1 < R ? 1 : 0)>(v, wt, reg_t);
+            if (j == 2) fan_apply<R, (2 < R ? 2 : 0)>(v, wt, reg_t);
+            if (j == 3) fan_apply<R, (3 < R ? 3 : 0)>(v, wt, reg_t);
+            if (j >= R) fan_apply<R, R>(v, wt, reg_t);
+          }
+#endif
         }
       }
 
+      {
+        // recomputed rather than kept live across the gate loop (register pressure)
+        uint32_t sr2[R];
 #pragma unroll
-      for (int rho = 0; rho < PER; ++rho) {
-        uint32_t s = st;
+        for (int k = 0; k < R; ++k) sr2[k] = swz(1u << byte_of(o_lo, o_hi, k));
+        const uint32_t st2 = swz(lt);
 #pragma unroll
-        for (int k = 0; k < R; ++k)
-          if ((rho >> k) & 1) s ^= sr[k];
-        sm[s] = v[rho];
+        for (int rho = 0; rho < PER; ++rho) {
+          uint32_t s = st2;
+#pragma unroll
+          for (int k = 0; k < R; ++k)
+            if ((rho >> k) & 1) s ^= sr2[k];
+          sm[s] = v[rho];
+        }
       }
       __syncthreads();
       rp += (rh >> 16);
     }
 
+    {
+      uint64_t hb[R];
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
-      uint64_t off = 0;
+      for (int k = 0; k < R; ++k) hb[k] = 1ull << byte_of(tb_lo, tb_hi, NTB + k);
 #pragma unroll
-      for (int k = 0; k < R; ++k)
-        if ((i >> k) & 1) off |= hb[k];
-      g[off] = sm[sw_t ^ swz_c((uint32_t)i * NT)];
+      for (int i = 0; i < PER; ++i) {
+        uint64_t off = 0;
+#pragma unroll
+        for (int k = 0; k < R; ++k)
+          if ((i >> k) & 1) off |= hb[k];
+        g[off] = sm[sw_t ^ swz_c((uint32_t)i * NT)];
+      }
     }
     __syncthreads();     // the next tile's cp.async must not overwrite slots still being read
   }
@@ -262,7 +392,9 @@ static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals)
     configured[st->device & 63] = true;
   }
   const uint64_t n_tiles = st->dim >> A;
-  const uint64_t cap = (uint64_t)kSMs * 64;
+  // persistent: exactly the resident CTAs, each walking tiles blockIdx, blockIdx + grid, ... so that it can
+  // prefetch its next tile into L2 while it works on the current one
+  const uint64_t cap = (uint64_t)kSMs * MINB;
   const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
   k_tile<A, R, MINB><<<grid, NT, smem, st->stream>>>(st->amp, n_tiles, st->index_offset, d_desc, d_reals);
   st->launches++;

@@ -105,6 +105,14 @@ def _mul(a: np.ndarray, b: np.ndarray) -> np.ndarray:
                      a[2] * b[0] + a[3] * b[2], a[2] * b[1] + a[3] * b[3]], dtype=complex)
 
 
+def _is_diag(m) -> bool:
+    return m[1] == 0 and m[2] == 0
+
+
+def _is_antidiag(m) -> bool:
+    return m[0] == 0 and m[3] == 0 and m[1] != 0 and m[2] != 0
+
+
 def _as_matrix(p: Prim) -> np.ndarray:
     if p.kind == "mat":
         return np.asarray(p.data, dtype=complex).reshape(4)
@@ -117,9 +125,12 @@ class Normalized:
     def __init__(self):
         self.items: List[Item] = []
         self.n_prims = 0
+        self.n_relabelled = 0                 # swap gates absorbed into the wire -> index-bit map
+        self.final_pos: List[int] = []        # wire -> index bit at the end of the segment
 
 
-def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = True) -> Normalized:
+def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = True,
+              relabel_swaps: bool = True) -> Normalized:
     out = Normalized()
     items = out.items
     pending: List[Optional[np.ndarray]] = [None] * n
@@ -188,6 +199,20 @@ def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = 
             return
         push(Item("phase", bits=bits, w=w, n_prims=count))
 
+    def emit_conjugated(bits: Tuple[int, ...], w: complex, count: int, done: Tuple[int, ...] = ()):
+        """Phase on `bits` arriving after pending anti-diagonal gates M_k = [[0, a], [b, 0]] on some of them:
+        phase(B + {k}, w) * M_k = M_k * phase(B, w) * phase(B + {k}, 1 / w)."""
+        for k in bits:
+            if k in done:
+                continue
+            m = pending[k]
+            if m is not None and _is_antidiag(m):
+                rest = tuple(b for b in bits if b != k)
+                emit_conjugated(rest, w, count, done)
+                emit_conjugated(bits, 1.0 / w, 0, done + (k,))
+                return
+        emit_phase(bits, w, count)
+
     def flush(q: int):
         m, cnt = pending[q], pending_count[q]
         pending[q], pending_count[q] = None, 0
@@ -205,55 +230,105 @@ def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = 
         else:
             push(Item("mat", t=q, m=m, n_prims=cnt), last_touch[q])
 
+    pos = list(range(n))                 # wire -> index bit its data lives on (swap gates only relabel)
     for p in prims:
         out.n_prims += 1
         if p.kind == "swap":
             a, b = p.target, p.aux
+            if relabel_swaps:
+                pos[a], pos[b] = pos[b], pos[a]
+                out.n_relabelled += 1
+                continue
             pending[a], pending[b] = pending[b], pending[a]
             pending_count[a], pending_count[b] = pending_count[b], pending_count[a]
             push(Item("swap", t=a, aux=b))
             continue
-        if not p.controls and fuse_1q:
+        tgt = pos[p.target]
+        ctrls = tuple(pos[cq] for cq in p.controls)
+        if not ctrls and fuse_1q:
             g = _as_matrix(p)
-            t = p.target
-            pending[t] = g if pending[t] is None else _mul(g, pending[t])
-            pending_count[t] += 1
+            pending[tgt] = g if pending[tgt] is None else _mul(g, pending[tgt])
+            pending_count[tgt] += 1
             continue
-        if not p.controls:
-            pending[p.target] = _as_matrix(p)
-            pending_count[p.target] = 1
-            flush(p.target)
+        if not ctrls:
+            pending[tgt] = _as_matrix(p)
+            pending_count[tgt] = 1
+            flush(tgt)
             continue
         # controlled gate: a diagonal pending factor commutes with a control, anything else is flushed first
-        for cq in p.controls:
-            m = pending[cq]
-            if m is not None and not (m[1] == 0 and m[2] == 0):
-                flush(cq)
         if p.kind == "diag":
-            m = pending[p.target]
-            if m is not None and not (m[1] == 0 and m[2] == 0):
-                flush(p.target)
             d0, d1 = complex(p.data[0]), complex(p.data[1])
+            qubits = ctrls + (tgt,)
+            if d0 != 1.0 and abs(d0) <= 0.5:            # not a phase pattern (non-unitary mat1-like payload)
+                for q in qubits:
+                    m = pending[q]
+                    if m is not None and not _is_diag(m):
+                        flush(q)
+                flush(tgt)
+                push(Item("mat", t=tgt, ctrls=ctrls, m=np.array([d0, 0, 0, d1], dtype=complex)))
+                continue
+            # a pending anti-diagonal 2x2 (X, Y, X*phase) need not be forced out either: P * M = M * P' with P'
+            # the phase conjugated by M, which is again a product of phases (emit_conjugated)
+            for q in qubits:
+                m = pending[q]
+                if m is not None and not _is_diag(m) and not _is_antidiag(m):
+                    flush(q)
             if d0 == 1.0:
-                emit_phase(p.controls + (p.target,), d1, 1)
-            elif abs(d0) > 0.5:
-                emit_phase(p.controls, d0, 1)
-                emit_phase(p.controls + (p.target,), d1 / d0, 0)
+                emit_conjugated(qubits, d1, 1)
             else:
-                flush(p.target)
-                push(Item("mat", t=p.target, ctrls=p.controls, m=np.array([d0, 0, 0, d1], dtype=complex)))
+                emit_conjugated(ctrls, d0, 1)
+                emit_conjugated(qubits, d1 / d0, 0)
             continue
-        flush(p.target)
+        for cq in ctrls:
+            m = pending[cq]
+            if m is not None and not _is_diag(m):
+                flush(cq)
+        flush(tgt)
         if p.kind == "x":
-            push(Item("x", t=p.target, ctrls=p.controls))
+            push(Item("x", t=tgt, ctrls=ctrls))
         else:
-            push(Item("mat", t=p.target, ctrls=p.controls, m=np.asarray(p.data, dtype=complex).reshape(4)))
+            push(Item("mat", t=tgt, ctrls=ctrls, m=np.asarray(p.data, dtype=complex).reshape(4)))
     for q in range(n):
         flush(q)
     if scalar[0] != 1.0:
-        push(Item("phase", bits=(), w=scalar[0], n_prims=0))
+        g = Item("phase", bits=(), w=scalar[0], n_prims=0)
+        g.pos = (-2, 0)                  # a global factor commutes with everything: ride along with the first pass
+        items.append(g)
     items.sort(key=lambda it: it.pos)
+    out.final_pos = pos
     return out
+
+
+def restore_involutions(final_pos: Sequence[int]) -> List[List[Tuple[int, int]]]:
+    """The data of wire w sits on index bit final_pos[w] and must end on bit w.  Returns at most two lists of
+    disjoint transpositions to apply in order: a bit permutation M (bit p moves to M(p)) is tau2 * tau1 with,
+    on every cycle c_0 -> c_1 -> ... -> c_(k-1) -> c_0, tau1: c_i <-> c_(-i) and tau2: c_i <-> c_(1-i)."""
+    n = len(final_pos)
+    move = [0] * n
+    for w, p in enumerate(final_pos):
+        move[p] = w
+    seen = [False] * n
+    t1: List[Tuple[int, int]] = []
+    t2: List[Tuple[int, int]] = []
+    for s0 in range(n):
+        if seen[s0] or move[s0] == s0:
+            seen[s0] = True
+            continue
+        cyc = []
+        q = s0
+        while not seen[q]:
+            seen[q] = True
+            cyc.append(q)
+            q = move[q]
+        k = len(cyc)
+        for i in range(k):
+            a, b = cyc[i], cyc[(-i) % k]
+            if a < b:
+                t1.append((a, b))
+            a, b = cyc[i], cyc[(1 - i) % k]
+            if a < b:
+                t2.append((a, b))
+    return [t for t in (t1, t2) if t]
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -418,10 +493,12 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int) -> None:
         """Encode one fan: fixed (mask, w) entries, local per-bit factors `lw`, optional target qubit."""
         fid = len(fan_records)
         lm = fm = skip = 0
+        jreg = r                                   # register bit of the target (r = none)
         if tgt is not None:
             if tgt in loc:
                 k = order.index(loc[tgt])
                 if k < r:
+                    jreg = k
                     skip = sum(1 << rho for rho in range(1 << r) if not (rho >> k) & 1)
                 else:
                     lm = 1 << loc[tgt]
@@ -446,7 +523,7 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int) -> None:
                 if (rho >> i) & 1 and order[i] in lw:
                     reg_t[rho] *= lw[order[i]]
         roff = prog.add_reals(list(lane_t) + list(warp_t) + list(reg_t))
-        return [K_FAN | (fid << 24) | (lm << 32) | (skip << 48), fm, roff]
+        return [K_FAN | (jreg << 8) | (fid << 24) | (lm << 32) | (skip << 48), fm, roff]
 
     encoded_rounds: List[Tuple[List[int], List[int]]] = []
     for rd in ps.rounds:
@@ -540,6 +617,7 @@ def plan(prims: Sequence[Prim], n_qubits: int, cfg: PlanConfig = DEFAULT) -> Pro
     if n < cfg.min_qubits:
         for it in norm.items:
             _emit_single(prog, it, n)
+        _emit_restore(prog, norm, n)
         return prog
     a = min(cfg.a, n)
     if a not in cfg.kernel_tiles:
@@ -556,4 +634,12 @@ def plan(prims: Sequence[Prim], n_qubits: int, cfg: PlanConfig = DEFAULT) -> Pro
             raise RuntimeError(f"planner made no progress at {remaining[0]}")
         encode_pass(prog, ps, n, r, c)
         remaining = rest
+    _emit_restore(prog, norm, n)
     return prog
+
+
+def _emit_restore(prog: Program, norm: Normalized, n: int) -> None:
+    for pairs in restore_involutions(norm.final_pos):
+        woff = prog.add_words([p | (q << 8) for p, q in pairs])
+        prog.add_op(_lib.OP_PERMUTE, woff=woff, wlen=len(pairs), nbytes=32.0 * 2 ** n)
+    prog.n_prims += norm.n_relabelled

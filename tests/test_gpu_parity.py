@@ -211,3 +211,34 @@ def test_tile_kernel_matches_descriptor_interpreter():
             got = dev.download()
             dev.close()
             assert maxabs(got, ref.psi) <= 1e-14
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 10, 11, 14, 18, 21])
+def test_permute_kernel_against_interpreter(n):
+    """In-place index-bit involutions (relabelled swap gates): random disjoint transpositions, bit reversal,
+    pairs among the low bits, the empty involution.  Pure data movement: bit exact."""
+    from oracle.program_interp import OracleState
+    from qaqarot_b200 import _lib
+    from qaqarot_b200.device import DeviceState
+    from qaqarot_b200.program import Program
+    rng = np.random.default_rng(n)
+    init = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
+    cases = [[(q, n - 1 - q) for q in range(n // 2)], []]
+    if n >= 4:
+        cases.append([(0, 1), (2, 3)])
+    for _ in range(6):
+        perm = [int(x) for x in rng.permutation(n)]
+        k = int(rng.integers(0, n // 2 + 1))
+        cases.append([(min(perm[2 * i], perm[2 * i + 1]), max(perm[2 * i], perm[2 * i + 1])) for i in range(k)])
+    for pairs in cases:
+        prog = Program()
+        woff = prog.add_words([p | (q << 8) for p, q in pairs])
+        prog.add_op(_lib.OP_PERMUTE, woff=woff, wlen=len(pairs))
+        dev, ref = DeviceState(n), OracleState(n)
+        dev.upload(init)
+        ref.upload(init)
+        dev.apply(prog)
+        ref.apply(prog)
+        got = dev.download()
+        dev.close()
+        assert np.array_equal(got, ref.psi), pairs

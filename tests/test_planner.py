@@ -59,12 +59,42 @@ def test_qft_becomes_fans():
     low = lower(W.qft(n).ops, n)
     norm = P.normalize(low.prims, n)
     kinds = [it.kind for it in norm.items]
-    # one 2x2 per qubit (X merged into H), one fan per qubit that has lower neighbours, the swaps
-    assert kinds.count("mat") == n and kinds.count("fan") == n - 1 and kinds.count("swap") == n // 2
-    assert sum(it.n_prims for it in norm.items) == len(low.prims)
+    # one 2x2 per qubit (X merged into H), one fan per qubit that has lower neighbours; the swaps only relabel
+    assert kinds.count("mat") == n and kinds.count("fan") == n - 1 and kinds.count("swap") == 0
+    assert norm.n_relabelled == n // 2 and norm.final_pos == list(range(n))[::-1]
+    assert sum(it.n_prims for it in norm.items) + norm.n_relabelled == len(low.prims)
     prog = P.plan(low.prims, n)
-    assert sum(1 for o in prog._ops if o[0] == _lib.OP_TILE) <= 3
+    kinds = [o[0] for o in prog._ops]
+    assert kinds.count(_lib.OP_TILE) <= 3 and kinds.count(_lib.OP_PERMUTE) == 1 and len(kinds) <= 4
     assert prog.n_prims == len(low.prims)
+
+
+def test_restore_involutions_compose_to_the_permutation():
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 5, 9, 16):
+        for _ in range(20):
+            final_pos = [int(x) for x in rng.permutation(n)]
+            bits = list(range(n))                      # bits[p] = wire whose data sits on index bit p
+            for w, p_ in enumerate(final_pos):
+                bits[p_] = w
+            invs = P.restore_involutions(final_pos)
+            assert len(invs) <= 2
+            for pairs in invs:
+                flat = [q for pq in pairs for q in pq]
+                assert len(set(flat)) == len(flat)
+                for a, b in pairs:
+                    bits[a], bits[b] = bits[b], bits[a]
+            assert bits == list(range(n))
+
+
+def test_swaps_are_relabelled_not_executed():
+    n = 10
+    c = Circuit(n).h[:].swap[0, 7].cx[0, 3].rz(0.3)[7].swap[2, 7].h[2].cz[7, 1].swap[0, 1].swap[5, 6].swap[5, 6]
+    be = interp_backend(P.PlanConfig(a=9))
+    ref = O.OracleBackend().run(c.ops, n)
+    assert maxabs(c.run(backend=be), ref) <= TOL
+    kinds = [o[0] for o in be._compiled.prefix._ops]
+    assert _lib.OP_SWAP not in kinds and _lib.OP_PERMUTE in kinds
 
 
 def test_one_qubit_chains_collapse():
