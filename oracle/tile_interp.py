@@ -10,8 +10,8 @@ from __future__ import annotations
 
 import numpy as np
 
-K_MAT, K_X, K_PHASE, K_FAN = 1, 2, 3, 4
-F_REAL = 1
+T_NONE, T_MATC, T_MATR, T_X = 0, 1, 2, 3
+D_NONE, D_FANT, D_FAN, D_PHASE = 0, 1, 2, 3
 
 
 def _unpack8(lo: int, hi: int, count: int):
@@ -33,10 +33,12 @@ def run_tile_pass(psi: np.ndarray, n: int, words: np.ndarray, reals: np.ndarray,
     tile = _unpack8(w[1], w[2], a)
     assert a <= n and tile == sorted(set(tile)) and tile[:c] == list(range(c)) and all(q < n for q in tile)
     dir_off, rounds_off = w[3] & 0xFFFFFFFF, w[3] >> 32
+    pay_lo, pay_len = w[4] & 0xFFFFFFFF, w[4] >> 32
+    assert dir_off == 5 and pay_lo + pay_len <= reals.size
     cre = reals.view(np.complex128) if reals.size % 2 == 0 else reals[:-1].view(np.complex128)
 
     def cplx(roff, count=1):
-        assert roff % 2 == 0 and roff // 2 + count <= cre.size, "payload offset out of range"
+        assert roff % 2 == 0 and pay_lo <= roff and roff + 2 * count <= pay_lo + pay_len, "payload offset out of range"
         return cre[roff // 2: roff // 2 + count]
 
     idx = np.arange(psi.size, dtype=np.uint64)
@@ -66,41 +68,44 @@ def run_tile_pass(psi: np.ndarray, n: int, words: np.ndarray, reals: np.ndarray,
         lane, warp = tid & np.uint64(31), tid >> np.uint64(5)
         g = pos + 3
         for _g in range(n_gates):
-            g0, fm, roff = w[g], np.uint64(w[g + 1]), w[g + 2]
+            g0, fm, roffs = w[g], np.uint64(w[g + 1]), w[g + 2]
             g += 3
-            kind, j, flags, fid = g0 & 0xFF, (g0 >> 8) & 0xFF, (g0 >> 16) & 0xFF, (g0 >> 24) & 0xFF
+            tk, j, dk, fid = g0 & 0xFF, (g0 >> 8) & 0xFF, (g0 >> 16) & 0xFF, (g0 >> 24) & 0xFF
             lm, rm = np.uint64((g0 >> 32) & 0xFFFF), np.uint64((g0 >> 48) & 0xFFFF)
+            roff_t, roff_d = roffs & 0xFFFFFFFF, roffs >> 32
             cond = ((fixed & fm) == fm) & ((local & lm) == lm)
-            if kind in (K_MAT, K_X):
-                assert j < r
-                cond &= (rho & rm) == rm
+            if tk != T_NONE:
+                assert j < r and dk in (D_NONE, D_FANT, D_FAN)
+                assert dk == D_NONE or (int(fm) == 0 and int(lm) == 0), "a fused fan must be unconditional"
+                c2 = cond & ((rho & rm) == rm)
                 tbit = np.uint64(1 << tile[order[j]])
-                i0 = idx[cond & ((idx & tbit) == 0)]
+                i0 = idx[c2 & ((idx & tbit) == 0)]
                 i1 = i0 | tbit
                 a0, a1 = psi[i0], psi[i1]
-                if kind == K_X:
+                if tk == T_X:
                     psi[i0], psi[i1] = a1, a0
                 else:
-                    m = cplx(roff, 4)
-                    if flags & F_REAL:
+                    m = cplx(roff_t, 4)
+                    if tk == T_MATR:
                         assert np.all(m.imag == 0)
                     psi[i0] = m[0] * a0 + m[1] * a1
                     psi[i1] = m[2] * a0 + m[3] * a1
-            elif kind == K_PHASE:
-                cond &= (rho & rm) == rm
-                psi[cond] *= cplx(roff)[0]
-            elif kind == K_FAN:
+            if dk in (D_FANT, D_FAN):
                 nt = a - r
                 n_warp = 1 << max(0, nt - 5)
-                tab = cplx(roff, 32 + n_warp + (1 << r))
+                tab = cplx(roff_d, 32 + n_warp + (1 << r if dk == D_FAN else 0))
                 lane_t, warp_t, reg_t = tab[:32], tab[32:32 + n_warp], tab[32 + n_warp:]
-                skip = int(rm)
-                keep = cond & (((np.uint64(skip) >> rho) & np.uint64(1)) == 0)
-                factor = fan_fixed[fid] * lane_t[lane.astype(np.int64)] * warp_t[warp.astype(np.int64)] \
-                    * reg_t[rho.astype(np.int64)]
+                keep = cond if j >= r else cond & (((rho >> np.uint64(j)) & np.uint64(1)) == 1)
+                factor = fan_fixed[fid] * lane_t[lane.astype(np.int64)] * warp_t[warp.astype(np.int64)]
+                if dk == D_FAN:
+                    factor = factor * reg_t[rho.astype(np.int64)]
                 psi[keep] *= factor[keep]
+            elif dk == D_PHASE:
+                assert tk == T_NONE
+                keep = cond & ((rho & rm) == rm)
+                psi[keep] *= cplx(roff_d)[0]
             else:
-                raise ValueError(f"unknown tile gate kind {kind}")
+                assert dk == D_NONE and tk != T_NONE, "empty gate record"
         assert g == pos + n_words, "round length mismatch"
         pos += n_words
     assert pos == len(w), "descriptor length mismatch"

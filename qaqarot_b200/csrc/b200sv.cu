@@ -489,7 +489,7 @@ int b200_apply_program(b200_state* st, const b200_op* ops, int n_ops, const uint
     if (st->profiling) { B200_CUDA(cudaEventRecord(st->op_events[2 * i], st->stream)); st->op_kinds[i] = op.kind; }
     if (op.kind == B200_OP_TILE) {
       B200_REQUIRE(op.woff + (uint64_t)op.wlen <= n_words, "TILE descriptor out of range");
-      if (launch_tile_pass(st, st->d_words + op.woff, words + op.woff, op.wlen, st->d_reals)) return 1;
+      if (launch_tile_pass(st, st->d_words + op.woff, words + op.woff, op.wlen, st->d_reals, n_reals)) return 1;
     } else if (op.kind == B200_OP_PERMUTE) {
       B200_REQUIRE(op.wlen >= 0 && op.woff + (uint64_t)op.wlen <= n_words, "PERMUTE descriptor out of range");
       if (launch_permute(st, words + op.woff, op.wlen)) return 1;

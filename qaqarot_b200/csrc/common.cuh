@@ -88,7 +88,7 @@ __host__ __device__ __forceinline__ uint64_t spread(uint64_t k, const BitPositio
 
 // tile.cu
 int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_desc, int wlen,
-                     const double* d_reals);
+                     const double* d_reals, size_t n_reals);
 
 // permute.cu
 int launch_permute(b200_state* st, const uint64_t* pairs, int n_pairs);

@@ -21,17 +21,20 @@
 //
 // Descriptor (uint64 words, produced by qaqarot_b200/planner.py::encode_pass; `reals` = float64 pool):
 //   D[0] = A | c<<8 | R<<16 | n_rounds<<24 | n_fans<<32          D[1], D[2] = tile bit positions, 8 bits each
-//   D[3] = fan directory offset | rounds offset << 32
+//   D[3] = fan directory offset | rounds offset << 32      D[4] = first payload real | payload length << 32
+//          (everything the pass reads from `reals` is that one range; each CTA keeps a copy in shared memory)
 //   fan directory: n_fans word offsets; fan record: n_entries | roff<<32, then n_entries masks.
 //       reals[roff] = w0, then one complex per entry.  Per tile: fix[f] = w0 * prod{w_e : mask_e subset of index}
-//   round: n_gates | n_words<<16, order[0..8), order[8..16), then 3 words per gate:
-//       G0 = kind | j<<8 | flags<<16 | fan<<24 | thread_mask<<32 | reg_mask<<48,  G1 = fixed-bit mask,  G2 = roff
-//     MAT  (1): 2x2 (reals[roff..+8), row major re/im) on register bit j where all masks are satisfied
-//     X    (2): pair swap on register bit j under the masks
-//     PHASE(3): amp *= reals[roff] where all masks are satisfied
-//     FAN  (4): amp *= fix[fan] * lane_t[lane] * warp_t[warp] * reg_t[rho] where register bit j of rho is set
-//               (j = R: every rho; reg_mask repeats this as a skip mask over rho for the interpreter)
-//               (tables at roff: 32 + 2^(A-R-5) + 2^R complex); thread_mask / fixed mask select the fan target
+//   round: n_gates | n_words<<16, order[0..8), order[8..16), then 3 words per gate record:
+//       G0 = target kind | j<<8 | diag kind<<16 | fan<<24 | thread_mask<<32 | reg_mask<<48,  G1 = fixed-bit mask,
+//       G2 = target payload offset | diag payload offset << 32  (into reals)
+//     A record runs where the fixed-bit mask (per tile) and the thread mask (per thread) are satisfied:
+//     target stage on register bit j:  1 = complex 2x2 (8 reals, row major re/im), 2 = real 2x2 (same layout),
+//                                      3 = pair swap; pairs whose other register bits satisfy reg_mask
+//     diag stage:  1 / 2 = fan  amp *= fix[fan] * lane_t[lane] * warp_t[warp] (* reg_t[rho] for kind 2) on the
+//                  amplitudes with register bit j set (j = R: all); tables 32 + 2^(A-R-5) (+ 2^R) complex
+//                  3 = phase  amp *= reals[offset] where rho satisfies reg_mask (never fused with a target stage)
+//     A 2x2 followed by a fan on the same register bit (the H + controlled-phase ladder of a QFT) is one record.
 #include "common.cuh"
 
 #include <cstdio>
@@ -39,7 +42,8 @@
 namespace b200 {
 
 constexpr int kMaxFans = 64;
-constexpr int K_MAT = 1, K_X = 2, K_PHASE = 3, K_FAN = 4;
+constexpr int T_NONE = 0, T_MATC = 1, T_MATR = 2, T_X = 3;
+constexpr int D_NONE = 0, D_FANT = 1, D_FAN = 2, D_PHASE = 3;
 
 __device__ __forceinline__ uint32_t swz(uint32_t l) {
   return l ^ ((l >> 3) & 7u) ^ ((l >> 6) & 7u) ^ ((l >> 9) & 7u) ^ ((l >> 12) & 7u);
@@ -59,6 +63,8 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* gmem_src, uint32_t 
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
+
+__host__ __device__ constexpr int ctz_c(int i) { return (i & 1) ? 0 : (i & 2) ? 1 : (i & 4) ? 2 : (i & 8) ? 3 : 4; }
 
 __device__ __forceinline__ int byte_of(uint64_t lo, uint64_t hi, int i) {
   return (int)(((i < 8 ? lo : hi) >> (8 * (i & 7))) & 0xFF);
@@ -161,45 +167,17 @@ __device__ __forceinline__ void perm_x(c128 (&v)[1 << R], uint32_t rm) {
   }
 }
 
-// One target gate on register bit J if it is the runtime target j.  Written as a chain of independent
-// `if (j == J)` blocks updating v in place (not a switch): every join then merges a value with itself, so the
-// register allocator keeps the 2^R amplitudes in place instead of shuffling them at the end of each case.
-template <int R, int J>
-__device__ __forceinline__ void apply_if(c128 (&v)[1 << R], int kind, bool real, int j, const double* m,
-                                         uint32_t rm) {
-  if (j != J) return;
-#ifndef EXP_NO_COND
-  if (rm == 0) {
-#endif
-#ifndef EXP_NO_PERMX
-    if (kind == K_X) perm_x<R, J, false>(v, 0);
-    else
-#endif
-#ifndef EXP_NO_MATC
-    if (real) mat_r<R, J, false>(v, m, 0);
-    else mat_c<R, J, false>(v, m, 0);
-#else
-    mat_r<R, J, false>(v, m, 0);
-#endif
-#ifndef EXP_NO_COND
-  } else {
-    if (kind == K_X) perm_x<R, J, true>(v, rm);
-    else if (real) mat_r<R, J, true>(v, m, rm);
-    else mat_c<R, J, true>(v, m, rm);
+// Fan on the amplitudes whose register bit K is set (K = R: every amplitude): per-thread factor only ...
+template <int R, int K>
+__device__ __forceinline__ void fant_apply(c128 (&v)[1 << R], c128 wt) {
+  const double nwy = -wt.y;
+#pragma unroll
+  for (int rho = 0; rho < (1 << R); ++rho) {
+    if (K < R && !((rho >> K) & 1)) continue;
+    amp_mul(v[rho], wt.x, wt.y, nwy);
   }
-#endif
 }
-
-template <int R>
-__device__ __forceinline__ void apply_target(c128 (&v)[1 << R], int kind, bool real, int j, const double* m,
-                                             uint32_t rm) {
-  apply_if<R, 0>(v, kind, real, j, m, rm);
-  if (R > 1) apply_if<R, (R > 1 ? 1 : 0)>(v, kind, real, j, m, rm);
-  if (R > 2) apply_if<R, (R > 2 ? 2 : 0)>(v, kind, real, j, m, rm);
-  if (R > 3) apply_if<R, (R > 3 ? 3 : 0)>(v, kind, real, j, m, rm);
-}
-
-// Fan on the amplitudes whose register bit K is set (K = R: every amplitude).
+// ... or with a further factor per register amplitude.
 template <int R, int K>
 __device__ __forceinline__ void fan_apply(c128 (&v)[1 << R], c128 wt, const double2* __restrict__ reg_t) {
 #pragma unroll
@@ -210,45 +188,156 @@ __device__ __forceinline__ void fan_apply(c128 (&v)[1 << R], c128 wt, const doub
   }
 }
 
+// Both stages of one record for register bit J (J = R: diag stage only).
+template <int R, int J, int NWARP_T>
+__device__ __forceinline__ void run_record(c128 (&v)[1 << R], uint32_t tk, bool cond, uint32_t dk, uint32_t rm,
+                                           const double* __restrict__ pay_t, const double* __restrict__ pay_d,
+                                           c128 wt) {
+  if constexpr (J < R) {
+    if (!cond) {
+      if (tk == T_MATR) mat_r<R, J, false>(v, pay_t, 0);
+      if (tk == T_MATC) mat_c<R, J, false>(v, pay_t, 0);
+      if (tk == T_X) perm_x<R, J, false>(v, 0);
+    } else {
+      if (tk == T_MATR) mat_r<R, J, true>(v, pay_t, rm);
+      if (tk == T_MATC) mat_c<R, J, true>(v, pay_t, rm);
+      if (tk == T_X) perm_x<R, J, true>(v, rm);
+    }
+  }
+  if (dk == D_FANT) fant_apply<R, J>(v, wt);
+  if (dk == D_FAN) fan_apply<R, J>(v, wt, reinterpret_cast<const double2*>(pay_d) + 32 + NWARP_T);
+  if constexpr (J >= R) {
+    if (dk == D_PHASE) {
+      const double wx = pay_d[0], wy = pay_d[1];
+#pragma unroll
+      for (int rho = 0; rho < (1 << R); ++rho)
+        if ((rho & rm) == rm) amp_mul(v[rho], wx, wy, -wy);
+    }
+  }
+}
+
+// ---- pre-decoded pass (built once per CTA in shared memory) ------------------------------------------------------
+// Decoding the planner's descriptor per gate, per thread, per tile cost ~60 instructions a gate in the first
+// version (ncu source view: a quarter of all issue slots).  The gate list is the same for every tile, so each
+// CTA decodes it once into 32-byte records and per-thread / per-round tables, and the tile loop only reads them.
+constexpr int kMaxGates = 160;     // per pass
+constexpr int kMaxRounds = 8;
+constexpr int kSpreadTabs = 5;     // 6 bits of the tile number each: up to 30 non-tile index bits
+
+constexpr int kMaxPayload = 3072;  // float64 payload of one pass kept in shared memory (planner.MAX_PAYLOAD)
+// record (one uint4): x = target kind | j<<4 | diag kind<<8 | (reg_mask != 0)<<12 | fan<<16 | fixed mask bits 32..39<<24
+//                     y = thread mask | reg mask<<16    z = target payload | diag payload<<16 (complex units, relative)
+//                     w = fixed mask bits 0..31
+
+struct RoundHdr {                  // 16 bytes
+  uint16_t n_gates, first;         // records [first, first + n_gates)
+  uint16_t srb[4];                 // slot XOR masks of the register bits: swz(1 << order[k])
+  uint32_t pad;
+};
+
+template <int A>
+struct TileSmem {
+  c128 tile[1 << A];
+  c128 fix[kMaxFans];
+  uint64_t spread[kSpreadTabs][64];
+  uint4 rec[kMaxGates + 1];
+  double pay[kMaxPayload];         // the pass's matrices, phases and fan tables
+  RoundHdr rh[kMaxRounds];
+  uint32_t thr[kMaxRounds][1 << (A - 4)];   // per round, per thread: local index bits | swizzled byte offset / 16 << 16
+  uint32_t round_off[kMaxRounds];
+};
+
 // ---- the kernel ------------------------------------------------------------------------------------------------
 template <int A, int R, int MINB>
 __global__ void __launch_bounds__(1 << (A - R), MINB)
 k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const uint64_t* __restrict__ desc,
        const double* __restrict__ reals) {
+  static_assert(R == 4, "the record dispatch assumes 4 register bits");
   constexpr int NT = 1 << (A - R), PER = 1 << R, NTB = A - R;
   constexpr int NWARP_T = (NTB > 5) ? (1 << (NTB - 5)) : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  c128* sm = reinterpret_cast<c128*>(smem_raw);
-  c128* fix = sm + (1 << A);
+  TileSmem<A>& S = *reinterpret_cast<TileSmem<A>*>(smem_raw);
+  c128* const sm = S.tile;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint64_t h0 = desc[0], tb_lo = desc[1], tb_hi = desc[2];
   const int n_rounds = (int)((h0 >> 24) & 0xFF), n_fans = (int)((h0 >> 32) & 0xFF);
   const uint32_t dir_off = (uint32_t)(desc[3] & 0xFFFFFFFFu), rounds_off = (uint32_t)(desc[3] >> 32);
+  const int c_bits = (int)((h0 >> 8) & 0xFF);
+  const uint32_t pay_lo = (uint32_t)(desc[4] & 0xFFFFFFFFu), pay_len = (uint32_t)(desc[4] >> 32);
 
+  // ---- one-time setup ----------------------------------------------------------------------------------------
+  if (tid == 0) {
+    uint32_t pos = rounds_off, first = 0;
+    for (int rd = 0; rd < n_rounds; ++rd) {
+      const uint64_t rh = desc[pos];
+      S.round_off[rd] = pos;
+      S.rh[rd].n_gates = (uint16_t)(rh & 0xFFFF);
+      S.rh[rd].first = (uint16_t)first;
+      first += (uint32_t)(rh & 0xFFFF);
+      pos += (uint32_t)(rh >> 16);
+    }
+  }
+  for (uint32_t i = tid; i < pay_len; i += NT) S.pay[i] = reals[pay_lo + i];
+  for (uint32_t idx = tid; idx < kSpreadTabs * 64; idx += NT) {
+    uint64_t x = (uint64_t)(idx & 63u) << (6 * (idx >> 6));
+    for (int i = 0; i < A; ++i) x = insert_zero(x, byte_of(tb_lo, tb_hi, i));
+    S.spread[idx >> 6][idx & 63u] = x;
+  }
+  __syncthreads();
+  for (int rd = 0; rd < n_rounds; ++rd) {
+    const uint64_t* __restrict__ rp = desc + S.round_off[rd];
+    const uint64_t o_lo = rp[1], o_hi = rp[2];
+    uint32_t lt = 0;
+    for (int b = 0; b < NTB; ++b) lt |= ((tid >> b) & 1u) << byte_of(o_lo, o_hi, R + b);
+    S.thr[rd][tid] = lt | (swz(lt) << 16);
+    if (tid < R) S.rh[rd].srb[tid] = (uint16_t)swz(1u << byte_of(o_lo, o_hi, tid));
+    const int ng = S.rh[rd].n_gates, first = S.rh[rd].first;
+    for (int gi = tid; gi < ng; gi += NT) {
+      const uint64_t g0 = rp[3 + 3 * gi], fm = rp[4 + 3 * gi], roffs = rp[5 + 3 * gi];
+      const uint32_t tk = (uint32_t)(g0 & 0xFF), j = (uint32_t)((g0 >> 8) & 0xFF), dk = (uint32_t)((g0 >> 16) & 0xFF);
+      const uint32_t fan = (uint32_t)((g0 >> 24) & 0xFF);
+      const uint32_t lm = (uint32_t)((g0 >> 32) & 0xFFFF), rm = (uint32_t)((g0 >> 48) & 0xFFFF);
+      const uint32_t pt = tk == T_NONE || tk == T_X ? 0u : (((uint32_t)roffs - pay_lo) >> 1);
+      const uint32_t pd = dk == D_NONE ? 0u : (((uint32_t)(roffs >> 32) - pay_lo) >> 1);
+      S.rec[first + gi] = make_uint4(tk | ((j > R ? R : j) << 4) | (dk << 8) | ((rm != 0 && tk != T_NONE) ? 1u << 12 : 0u) |
+                                         (fan << 16) | ((uint32_t)(fm >> 32) << 24),
+                                     lm | (rm << 16), pt | (pd << 16), (uint32_t)fm);
+    }
+  }
   // copy phases: thread handles local indices l = i * NT + tid; off_t / hb[] deposit l into index positions
   uint64_t off_t = 0;
 #pragma unroll
   for (int b = 0; b < NTB; ++b) off_t |= (uint64_t)((tid >> b) & 1u) << byte_of(tb_lo, tb_hi, b);
-  const uint32_t sw_t = swz(tid);
-  // rows of 2^c contiguous amplitudes; this thread prefetches rows tid, tid + NT, ... of the *next* tile into L2
-  const int c_bits = (int)((h0 >> 8) & 0xFF);
+  const uint32_t sw_t = swz(tid) << 4;              // byte offset of this thread's slot for i = 0
+  // rows of 2^c contiguous amplitudes; this thread prefetches row(s) tid, tid + NT, ... of its *next* tile into L2
   const uint32_t n_rows = 1u << (A - c_bits), row_bytes = 16u << c_bits;
+  uint64_t pref_off = 0;
+  for (int b = c_bits; b < A; ++b) pref_off |= (uint64_t)((tid >> (b - c_bits)) & 1u) << byte_of(tb_lo, tb_hi, b);
+  __syncthreads();
+
+  auto spread_tile = [&](uint64_t t) -> uint64_t {
+    uint64_t b = S.spread[0][t & 63u];
+#pragma unroll
+    for (int j = 1; j < kSpreadTabs; ++j) b |= S.spread[j][(t >> (6 * j)) & 63u];
+    return b;
+  };
 
   for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    uint64_t base = tile;
-#pragma unroll
-    for (int i = 0; i < A; ++i) base = insert_zero(base, byte_of(tb_lo, tb_hi, i));
+    const uint64_t base = spread_tile(tile);
     const uint64_t fixedidx = base | index_offset;
+    const uint32_t fx_lo = (uint32_t)fixedidx, fx_hi = (uint32_t)(fixedidx >> 32);
     c128* __restrict__ g = amp + base + off_t;
     if (tile + gridDim.x < n_tiles) {
-      uint64_t nbase = tile + gridDim.x;
-#pragma unroll
-      for (int i = 0; i < A; ++i) nbase = insert_zero(nbase, byte_of(tb_lo, tb_hi, i));
-      for (uint32_t row = tid; row < n_rows; row += NT) {
-        uint64_t roff = 0;
-        for (int b = c_bits; b < A; ++b) roff |= (uint64_t)((row >> (b - c_bits)) & 1u) << byte_of(tb_lo, tb_hi, b);
-        prefetch_l2_bulk(amp + nbase + roff, row_bytes);
+      const c128* nb = amp + spread_tile(tile + gridDim.x);
+      if (n_rows == (uint32_t)NT) {
+        prefetch_l2_bulk(nb + pref_off, row_bytes);
+      } else {
+        for (uint32_t row = tid; row < n_rows; row += NT) {
+          uint64_t roff = 0;
+          for (int b = c_bits; b < A; ++b) roff |= (uint64_t)((row >> (b - c_bits)) & 1u) << byte_of(tb_lo, tb_hi, b);
+          prefetch_l2_bulk(nb + roff, row_bytes);
+        }
       }
     }
 
@@ -262,7 +351,7 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
 #pragma unroll
         for (int k = 0; k < R; ++k)
           if ((i >> k) & 1) off |= hb[k];
-        cp_async16(&sm[sw_t ^ swz_c((uint32_t)i * NT)], g + off);
+        cp_async16(reinterpret_cast<unsigned char*>(sm) + (sw_t ^ (swz_c((uint32_t)i * NT) << 4)), g + off);
       }
     }
 
@@ -271,7 +360,7 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
       const uint32_t off = (uint32_t)desc[dir_off + f];
       const uint64_t rec = desc[off];
       const int ne = (int)(rec & 0xFFFFFFFFu);
-      const double2* __restrict__ w = reinterpret_cast<const double2*>(reals + (rec >> 32));
+      const double2* __restrict__ w = reinterpret_cast<const double2*>(S.pay + ((uint32_t)(rec >> 32) - pay_lo));
       c128 p = make_double2(1.0, 0.0);
       for (int e = (int)lane; e < ne; e += 32) {
         const uint64_t m = desc[off + 1 + e];
@@ -284,85 +373,65 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
         q.y = __shfl_xor_sync(0xffffffffu, p.y, o);
         p = cmul(p, q);
       }
-      if (lane == 0) fix[f] = cmul(p, w[0]);
+      if (lane == 0) S.fix[f] = cmul(p, w[0]);
     }
     cp_async_wait_all();
     __syncthreads();
 
-    const uint64_t* __restrict__ rp = desc + rounds_off;
     for (int rd = 0; rd < n_rounds; ++rd) {
-      const uint64_t rh = rp[0], o_lo = rp[1], o_hi = rp[2];
-      const int ng = (int)(rh & 0xFFFF);
-      uint32_t lt = 0;
-#pragma unroll
-      for (int b = 0; b < NTB; ++b) lt |= ((tid >> b) & 1u) << byte_of(o_lo, o_hi, R + b);
-      uint32_t sr[R];
-#pragma unroll
-      for (int k = 0; k < R; ++k) sr[k] = swz(1u << byte_of(o_lo, o_hi, k));
-      const uint32_t st = swz(lt);
+      const uint4 hq = *reinterpret_cast<const uint4*>(&S.rh[rd]);
+      const int ng = (int)(hq.x & 0xFFFFu), first = (int)(hq.x >> 16);
+      const uint32_t srb[4] = {(hq.y & 0xFFFFu) << 4, (hq.y >> 16) << 4, (hq.z & 0xFFFFu) << 4, (hq.z >> 16) << 4};
+      const uint32_t my = S.thr[rd][tid];
+      const uint32_t lt = my & 0xFFFFu, stb = (my >> 16) << 4;
+      unsigned char* const smb = reinterpret_cast<unsigned char*>(sm);
 
+      // Gray-code walk over the 2^R register amplitudes: one XOR per shared-memory address
       c128 v[PER];
+      {
+        uint32_t s = stb;
 #pragma unroll
-      for (int rho = 0; rho < PER; ++rho) {
-        uint32_t s = st;
-#pragma unroll
-        for (int k = 0; k < R; ++k)
-          if ((rho >> k) & 1) s ^= sr[k];
-        v[rho] = sm[s];
+        for (int i = 0; i < PER; ++i) {
+          if (i) s ^= srb[ctz_c(i)];
+          v[i ^ (i >> 1)] = *reinterpret_cast<const c128*>(smb + s);
+        }
       }
 
-      // One structured body per gate, no `continue`: with early exits ptxas split the live ranges of the whole
-      // register tile at the loop head and copied all 2^R amplitudes twice per gate.
-      const uint64_t* __restrict__ gp = rp + 3;
-      for (int gi = 0; gi < ng; ++gi, gp += 3) {
-        const uint64_t g0 = gp[0], fm = gp[1];
-        const uint32_t lm = (uint32_t)((g0 >> 32) & 0xFFFF), rm = (uint32_t)((g0 >> 48) & 0xFFFF);
+      // the next record is fetched while the current one runs
+      uint4 q = S.rec[first];
+      for (int gi = first; gi < first + ng; ++gi) {
+        const uint4 nq = S.rec[gi + 1];
+        const uint32_t lm = q.y & 0xFFFFu, rm = q.y >> 16, fmh = q.x >> 24;
         // fixed-bit condition: CTA-uniform; thread-bit condition: per thread
-        const bool active = ((fixedidx & fm) == fm) && ((lt & lm) == lm);
+        const bool active = ((fx_lo & q.w) == q.w) && ((fx_hi & fmh) == fmh) && ((lt & lm) == lm);
         if (active) {
-          const double* __restrict__ pay = reals + gp[2];
-          const int kind = (int)(g0 & 0xFF), j = (int)((g0 >> 8) & 0xFF);
-          if (kind == K_MAT || kind == K_X) apply_target<R>(v, kind, ((g0 >> 16) & 1) != 0, j, pay, rm);
-#ifndef EXP_NO_PHASE
-          if (kind == K_PHASE) {
-            const double wx = pay[0], wy = pay[1];
-#pragma unroll
-            for (int rho = 0; rho < PER; ++rho)
-              if ((rho & rm) == rm) amp_mul(v[rho], wx, wy, -wy);
+          const uint32_t tk = q.x & 15u, j = (q.x >> 4) & 15u, dk = (q.x >> 8) & 15u;
+          const bool cond = ((q.x >> 12) & 1u) != 0;
+          const double* __restrict__ pay_t = S.pay + 2 * (q.z & 0xFFFFu);
+          const double* __restrict__ pay_d = S.pay + 2 * (q.z >> 16);
+          c128 wt = make_double2(1.0, 0.0);
+          if (dk == D_FANT || dk == D_FAN) {
+            const double2* __restrict__ tab = reinterpret_cast<const double2*>(pay_d);
+            wt = cmul(S.fix[(q.x >> 16) & 0xFFu], cmul(tab[lane], tab[32 + (NWARP_T > 1 ? warp : 0)]));
           }
-#endif
-#ifndef EXP_NO_FAN
-          if (kind == K_FAN) {
-            const double2* __restrict__ tab = reinterpret_cast<const double2*>(pay);
-            const c128 wt = cmul(fix[(g0 >> 24) & 0xFF], cmul(tab[lane], tab[32 + (NWARP_T > 1 ? warp : 0)]));
-            const double2* __restrict__ reg_t = tab + 32 + NWARP_T;
-            if (j == 0) fan_apply<R, 0>(v, wt, reg_t);
-            if (j == 1) fan_apply<R, (1 < R ? 1 : 0)>(v, wt, reg_t);
-            if (j == 2) fan_apply<R, (2 < R ? 2 : 0)>(v, wt, reg_t);
-            if (j == 3) fan_apply<R, (3 < R ? 3 : 0)>(v, wt, reg_t);
-            if (j >= R) fan_apply<R, R>(v, wt, reg_t);
-          }
-#endif
+          if (j == 0) run_record<R, 0, NWARP_T>(v, tk, cond, dk, rm, pay_t, pay_d, wt);
+          if (j == 1) run_record<R, 1, NWARP_T>(v, tk, cond, dk, rm, pay_t, pay_d, wt);
+          if (j == 2) run_record<R, 2, NWARP_T>(v, tk, cond, dk, rm, pay_t, pay_d, wt);
+          if (j == 3) run_record<R, 3, NWARP_T>(v, tk, cond, dk, rm, pay_t, pay_d, wt);
+          if (j >= R) run_record<R, R, NWARP_T>(v, tk, cond, dk, rm, pay_t, pay_d, wt);
         }
+        q = nq;
       }
 
       {
-        // recomputed rather than kept live across the gate loop (register pressure)
-        uint32_t sr2[R];
+        uint32_t s = stb;
 #pragma unroll
-        for (int k = 0; k < R; ++k) sr2[k] = swz(1u << byte_of(o_lo, o_hi, k));
-        const uint32_t st2 = swz(lt);
-#pragma unroll
-        for (int rho = 0; rho < PER; ++rho) {
-          uint32_t s = st2;
-#pragma unroll
-          for (int k = 0; k < R; ++k)
-            if ((rho >> k) & 1) s ^= sr2[k];
-          sm[s] = v[rho];
+        for (int i = 0; i < PER; ++i) {
+          if (i) s ^= srb[ctz_c(i)];
+          *reinterpret_cast<c128*>(smb + s) = v[i ^ (i >> 1)];
         }
       }
       __syncthreads();
-      rp += (rh >> 16);
     }
 
     {
@@ -375,7 +444,7 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
 #pragma unroll
         for (int k = 0; k < R; ++k)
           if ((i >> k) & 1) off |= hb[k];
-        g[off] = sm[sw_t ^ swz_c((uint32_t)i * NT)];
+        g[off] = *reinterpret_cast<const c128*>(reinterpret_cast<unsigned char*>(sm) + (sw_t ^ (swz_c((uint32_t)i * NT) << 4)));
       }
     }
     __syncthreads();     // the next tile's cp.async must not overwrite slots still being read
@@ -385,7 +454,7 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
 template <int A, int R, int MINB>
 static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals) {
   constexpr int NT = 1 << (A - R);
-  const size_t smem = sizeof(c128) * ((size_t(1) << A) + kMaxFans);
+  const size_t smem = sizeof(TileSmem<A>);
   static bool configured[64] = {};
   if (!configured[st->device & 63]) {
     B200_CUDA(cudaFuncSetAttribute(k_tile<A, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -403,15 +472,16 @@ static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals)
 }
 
 int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_desc, int wlen,
-                     const double* d_reals) {
-  B200_REQUIRE(wlen >= 4, "TILE descriptor too short");
+                     const double* d_reals, size_t n_reals) {
+  B200_REQUIRE(wlen >= 5, "TILE descriptor too short");
   const uint64_t h0 = h_desc[0];
   const int A = (int)(h0 & 0xFF), c = (int)((h0 >> 8) & 0xFF), R = (int)((h0 >> 16) & 0xFF);
-  const int n_fans = (int)((h0 >> 32) & 0xFF);
+  const int n_rounds = (int)((h0 >> 24) & 0xFF), n_fans = (int)((h0 >> 32) & 0xFF);
   char msg[200];
-  if (A > st->n || c > A || R != 4 || n_fans > kMaxFans) {
-    snprintf(msg, sizeof msg, "TILE descriptor not executable: A=%d c=%d R=%d fans=%d on %d qubits", A, c, R, n_fans,
-             st->n);
+  if (A > st->n || c > A || R != 4 || n_fans > kMaxFans || n_rounds > kMaxRounds ||
+      st->n - A > 6 * kSpreadTabs) {
+    snprintf(msg, sizeof msg, "TILE descriptor not executable: A=%d c=%d R=%d fans=%d rounds=%d on %d qubits", A, c, R,
+             n_fans, n_rounds, st->n);
     set_error(msg);
     return 1;
   }
@@ -427,6 +497,15 @@ int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_d
   const uint64_t dir_off = h_desc[3] & 0xFFFFFFFFu, rounds_off = h_desc[3] >> 32;
   B200_REQUIRE(dir_off + (uint64_t)n_fans <= (uint64_t)wlen && rounds_off <= (uint64_t)wlen,
                "TILE descriptor: offsets out of range");
+  B200_REQUIRE((h_desc[4] >> 32) <= (uint64_t)kMaxPayload && (h_desc[4] & 0xFFFFFFFFu) + (h_desc[4] >> 32) <= n_reals,
+               "TILE descriptor: payload range too long or outside the reals pool");
+  uint64_t pos = rounds_off, gates = 0;
+  for (int rd = 0; rd < n_rounds; ++rd) {
+    B200_REQUIRE(pos + 3 <= (uint64_t)wlen, "TILE descriptor: round header out of range");
+    gates += h_desc[pos] & 0xFFFF;
+    pos += h_desc[pos] >> 16;
+  }
+  B200_REQUIRE(pos == (uint64_t)wlen && gates <= (uint64_t)kMaxGates, "TILE descriptor: bad round lengths or too many gates");
   switch (A) {
     case 9:  return launch<9, 4, 8>(st, d_desc, d_reals);
     case 10: return launch<10, 4, 8>(st, d_desc, d_reals);

@@ -31,8 +31,10 @@ from . import _lib
 from .lowering import Prim
 from .program import Program
 
-K_MAT, K_X, K_PHASE, K_FAN = 1, 2, 3, 4
-F_REAL = 1
+T_NONE, T_MATC, T_MATR, T_X = 0, 1, 2, 3          # target stage of a tile gate record
+D_NONE, D_FANT, D_FAN, D_PHASE = 0, 1, 2, 3         # diagonal stage (fan without / with register table, phase)
+MAX_GATES = 160          # per pass (record slots in csrc/tile.cu)
+MAX_PAYLOAD = 3072       # float64 payload of one pass (shared-memory copy in csrc/tile.cu)
 MAX_FANS = 64            # per pass (shared-memory slots in csrc/tile.cu)
 
 
@@ -348,6 +350,17 @@ def _cost(it: Item) -> float:
     return 0.0
 
 
+def _payload(it: Item, a: int, r: int) -> int:
+    """Upper bound of the float64 payload an item adds to its pass."""
+    if it.kind == "mat":
+        return 8
+    if it.kind == "phase":
+        return 4
+    if it.kind == "fan":
+        return 2 * (2 + len(it.entries) + 32 + (1 << max(0, a - r - 5)) + 2 * (1 << r))
+    return 0
+
+
 @dataclass
 class Round:
     reg: List[int]                       # physical qubits held in registers (r of them)
@@ -377,6 +390,8 @@ def build_pass(remaining: List[Item], n: int, a: int, r: int, c: int, cfg: PlanC
     done = [False] * len(remaining)
     cost = 0.0
     n_fans = 0
+    n_gates = 0
+    payload = 0
     limit = min(len(remaining), cfg.scan_limit)
     for _ in range(cfg.max_rounds):
         reg: List[int] = []
@@ -388,7 +403,9 @@ def build_pass(remaining: List[Item], n: int, a: int, r: int, c: int, cfg: PlanC
                 continue
             it = remaining[idx]
             ok = it.kind != "swap" and not _conflict(it, skipped_nd, skipped_dg)
-            if ok and it.kind == "fan" and n_fans >= MAX_FANS - 1:
+            pay = _payload(it, a, r)
+            if ok and ((it.kind == "fan" and n_fans >= MAX_FANS - 1) or n_gates + 2 >= MAX_GATES - 1
+                       or payload + pay > MAX_PAYLOAD - 64):
                 ok = False
             if ok and it.nd:
                 t = it.t
@@ -405,6 +422,8 @@ def build_pass(remaining: List[Item], n: int, a: int, r: int, c: int, cfg: PlanC
                 picked.append(idx)
                 cost += _cost(it)
                 n_fans += it.kind == "fan"
+                n_gates += 2 if it.kind == "fan" else 1
+                payload += pay
             else:
                 skipped_nd |= it.nd
                 skipped_dg |= it.dg
@@ -488,18 +507,22 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int) -> None:
         return lm, rm, fm
 
     scalars: List[Tuple[int, complex]] = []     # (fixed-bit mask, factor): diagonal gates constant over a tile
+    pay_lo = len(prog._reals)                   # everything this pass appends to `reals` is one contiguous range
 
-    def fan_gate(order, fid_entries, w0, lw, tgt) -> List[int]:
-        """Encode one fan: fixed (mask, w) entries, local per-bit factors `lw`, optional target qubit."""
+    def gate_words(tk=T_NONE, j=None, dk=D_NONE, fid=0, lm=0, rm=0, fm=0, roff_t=0, roff_d=0) -> List[int]:
+        j = r if j is None else j
+        return [tk | (j << 8) | (dk << 16) | (fid << 24) | (lm << 32) | (rm << 48), fm, roff_t | (roff_d << 32)]
+
+    def fan_fields(order, fid_entries, w0, lw, tgt) -> dict:
+        """One fan: fixed (mask, w) entries, local per-bit factors `lw`, optional target qubit -> gate fields."""
         fid = len(fan_records)
-        lm = fm = skip = 0
+        lm = fm = 0
         jreg = r                                   # register bit of the target (r = none)
         if tgt is not None:
             if tgt in loc:
                 k = order.index(loc[tgt])
                 if k < r:
                     jreg = k
-                    skip = sum(1 << rho for rho in range(1 << r) if not (rho >> k) & 1)
                 else:
                     lm = 1 << loc[tgt]
             else:
@@ -522,34 +545,42 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int) -> None:
             for i in range(r):
                 if (rho >> i) & 1 and order[i] in lw:
                     reg_t[rho] *= lw[order[i]]
-        roff = prog.add_reals(list(lane_t) + list(warp_t) + list(reg_t))
-        return [K_FAN | (jreg << 8) | (fid << 24) | (lm << 32) | (skip << 48), fm, roff]
+        if np.any(reg_t != 1.0):
+            return dict(j=jreg, dk=D_FAN, fid=fid, lm=lm, fm=fm,
+                        roff_d=prog.add_reals(list(lane_t) + list(warp_t) + list(reg_t)))
+        return dict(j=jreg, dk=D_FANT, fid=fid, lm=lm, fm=fm, roff_d=prog.add_reals(list(lane_t) + list(warp_t)))
 
     encoded_rounds: List[Tuple[List[int], List[int]]] = []
     for rd in ps.rounds:
         order = _thread_order(tile, rd.reg)
         gates: List[int] = []
+        pending_t: Optional[dict] = None          # target stage waiting for a fan on the same register bit
+
+        def flush_t():
+            nonlocal pending_t
+            if pending_t is not None:
+                gates.extend(gate_words(**pending_t))
+                pending_t = None
+
         for it in rd.items:
             n_prims += it.n_prims
             if it.kind in ("mat", "x"):
+                flush_t()
                 j = order.index(loc[it.t])
                 assert j < r, "non-diagonal target outside the round's register bits"
                 lm, rm, fm = split_mask(it.ctrls, order)
                 if it.kind == "mat":
                     real = bool(np.all(np.asarray(it.m).imag == 0))
-                    roff = prog.add_reals(it.m)
-                    g0 = K_MAT | (j << 8) | ((F_REAL if real else 0) << 16) | (lm << 32) | (rm << 48)
+                    pending_t = dict(tk=T_MATR if real else T_MATC, j=j, lm=lm, rm=rm, fm=fm, roff_t=prog.add_reals(it.m))
                 else:
-                    roff = 0
-                    g0 = K_X | (j << 8) | (lm << 32) | (rm << 48)
-                gates += [g0, fm, roff]
+                    pending_t = dict(tk=T_X, j=j, lm=lm, rm=rm, fm=fm)
             elif it.kind == "phase":
                 if not any(q in loc for q in it.bits):
                     scalars.append((sum(1 << q for q in it.bits), it.w))
                     continue
+                flush_t()
                 lm, rm, fm = split_mask(it.bits, order)
-                roff = prog.add_reals([it.w])
-                gates += [K_PHASE | (lm << 32) | (rm << 48), fm, roff]
+                gates += gate_words(dk=D_PHASE, lm=lm, rm=rm, fm=fm, roff_d=prog.add_reals([it.w]))
             else:                                           # fan
                 if it.t not in loc and not any(q in loc for q in it.entries):
                     scalars.append((1 << it.t, it.w))
@@ -557,11 +588,20 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int) -> None:
                     continue
                 fixed = [(1 << q, w) for q, w in it.entries.items() if q not in loc]
                 lw = {loc[q]: w for q, w in it.entries.items() if q in loc}
-                gates += fan_gate(order, fixed, it.w, lw, it.t)
+                f = fan_fields(order, fixed, it.w, lw, it.t)
+                if (pending_t is not None and pending_t["j"] == f["j"] and f["j"] < r and pending_t["lm"] == 0
+                        and pending_t["fm"] == 0):
+                    # 2x2 on a register bit followed by a fan on the same bit: one record, one dispatch
+                    pending_t.update(dk=f["dk"], fid=f["fid"], roff_d=f["roff_d"])
+                    flush_t()
+                else:
+                    flush_t()
+                    gates += gate_words(**f)
+        flush_t()
         encoded_rounds.append((order, gates))
     if scalars:
         order, gates = encoded_rounds[-1]
-        gates += fan_gate(order, scalars, 1.0 + 0j, {}, None)
+        gates += gate_words(**fan_fields(order, scalars, 1.0 + 0j, {}, None))
     for order, gates in encoded_rounds:
         o_lo, o_hi = _pack8(order)
         round_words += [(len(gates) // 3) | ((3 + len(gates)) << 16), o_lo, o_hi] + gates
@@ -571,13 +611,15 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int) -> None:
     n_fans = len(fan_records)
     directory: List[int] = []
     body: List[int] = []
-    base = 4 + n_fans
+    pay_len = len(prog._reals) - pay_lo
+    assert pay_len <= MAX_PAYLOAD and sum(len(g) // 3 for _, g in encoded_rounds) <= MAX_GATES
+    base = 5 + n_fans
     for rec in fan_records:
         directory.append(base + len(body))
         body += rec
     rounds_off = base + len(body)
     words = [a | (c << 8) | (r << 16) | (len(ps.rounds) << 24) | (n_fans << 32), t_lo, t_hi,
-             4 | (rounds_off << 32)] + directory + body + round_words
+             5 | (rounds_off << 32), pay_lo | (pay_len << 32)] + directory + body + round_words
     woff = prog.add_words(words)
     prog.add_op(_lib.OP_TILE, woff=woff, wlen=len(words), nbytes=32.0 * 2 ** n)
     prog.n_prims += n_prims
