@@ -105,22 +105,34 @@ def build_workload(name: str, n: int, depth: int):
 # ---------------------------------------------------------------------------------------------------
 # CPU path (numpy port of the reference), on a bounded sample of the workload's gate list
 def cpu_sample(circ, n: int, budget_s: float):
-    """Every `stride`-th op of the gate list, stride chosen so the predicted cost fits the budget.
-    Per-op cost model (seconds at 26 qubits on one core, scaled by 2^(n-26)): full-state 2x2 passes ~0.9,
-    controlled-diagonal quarter passes ~0.065."""
+    """A stratified sample of the gate list: the same fraction of every gate kind (evenly spaced within the kind,
+    program order kept), the fraction chosen so that the predicted cost fits the budget.
+    Per-op cost model (seconds at 26 qubits on one core, scaled by 2^(n-26)), from runs of the numpy port:
+    full-state 2x2 passes ~0.9, controlled-diagonal quarter passes ~0.065."""
     scale = 2.0 ** (n - 26)
-    cost = {"h": 0.95, "x": 0.85, "swap": 0.85 * 3, "cphase": 0.065, "rz": 0.5, "cx": 0.6}
+    cost = {"h": 0.95, "x": 0.85, "swap": 0.85, "cphase": 0.065, "rz": 0.5, "cx": 0.6, "rx": 0.95}
     ops = list(circ.ops)
-    per_op = [cost.get(o.lowername, 0.9) * scale for o in ops]
-    stride = 1
-    while stride < len(ops) and sum(per_op[stride // 2::stride]) > budget_s:
-        stride += 1
-    picked = ops[stride // 2::stride]
+    by_kind = {}
+    for i, o in enumerate(ops):
+        by_kind.setdefault(o.lowername, []).append(i)
+    total = sum(cost.get(k, 0.9) * scale * len(v) for k, v in by_kind.items())
+    frac = min(1.0, budget_s / total)
+    picked_idx = []
+    for k, idxs in by_kind.items():
+        m = int(round(len(idxs) * frac))
+        if m == 0 and len(idxs) * frac >= 0.35:
+            m = 1
+        if m:
+            step = len(idxs) / m
+            picked_idx += [idxs[int((j + 0.5) * step)] for j in range(m)]
+    picked_idx.sort()
+    picked = [ops[i] for i in picked_idx]
     names = {}
     for o in picked:
         names[o.lowername] = names.get(o.lowername, 0) + 1
-    desc = (f"every {stride}th op of the {len(ops)}-op gate list at n={n} "
-            f"({', '.join(f'{v} {k}' for k, v in sorted(names.items()))}) on a numpy port of NumPyBackend")
+    desc = (f"{len(picked)} of the {len(ops)} ops of the gate list at n={n}, the same fraction of every gate kind "
+            f"({', '.join(f'{v} {k}' for k, v in sorted(names.items()))}), on a dense random state, "
+            f"numpy port of NumPyBackend")
     return picked, desc
 
 
@@ -146,7 +158,6 @@ def time_cpu_path(circ, n: int, budget_s: float, steps: int = 1, warmup: int = 0
     if n_cpu != n:
         raise SystemExit(f"host RAM too small for a {n}-qubit CPU sample (needs {need_gib:.0f} GiB)")
     picked, desc = cpu_sample(circ, n, budget_s)
-    gates = lower(picked, n).n_gates
     ctx = O.Ctx(n)
     ctx.prepare(None)
     rng = np.random.default_rng(0)
@@ -155,31 +166,58 @@ def time_cpu_path(circ, n: int, budget_s: float, steps: int = 1, warmup: int = 0
     for off in range(0, 1 << n, blk):
         m = min(blk, (1 << n) - off)
         ctx.qubits[off:off + m] = (rng.standard_normal(m) + 1j * rng.standard_normal(m)) * (2.0 ** (-(n + 1) / 2))
-    times = []
+    # time every sampled op; the whole-list time is extrapolated per gate kind (count_k * mean seconds of kind k)
+    kinds = {}
+    for o in circ.ops:
+        kinds[o.lowername] = kinds.get(o.lowername, 0) + 1
+    all_gates = lower(list(circ.ops), n).n_gates
+    est = []
     for it in range(warmup + steps):
-        t0 = time.perf_counter()
+        per_kind = {}
         for op in picked:
+            t0 = time.perf_counter()
             O.run_gate(ctx, op)
-        dt = time.perf_counter() - t0
+            per_kind.setdefault(op.lowername, []).append(time.perf_counter() - t0)
         if it >= warmup:
-            times.append(dt)
-    sec = float(np.mean(times))
-    return gates / sec, desc, sec
+            fallback = float(np.mean([t for v in per_kind.values() for t in v]))
+            est.append(sum(cnt * (float(np.mean(per_kind[k])) if k in per_kind else fallback) for k, cnt in kinds.items()))
+    sec_full = float(np.mean(est))
+    sampled_sec = sum(sum(v) for v in per_kind.values())
+    desc += (f"; per-kind mean op times extrapolated to the full {len(circ.ops)}-op list "
+             f"({sampled_sec:.1f} s of CPU work per step sampled, {sec_full:.0f} s extrapolated)")
+    return all_gates / sec_full, desc, sampled_sec
 
 
 # ---------------------------------------------------------------------------------------------------
 def run_reference(args):
+    """The CPU path on this arm's config.  Under torchrun only rank 0 works.  A register that does not fit the
+    host (33 / 36 qubits need 128 GiB / 1 TiB plus numpy temporaries) is timed at the largest size that does and
+    scaled by the state-size ratio: every numpy gate pass is linear in 2^n."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    circ, wl = build_workload(args.workload, args.qubits, args.depth)
+    if world > 1:
+        wname, n, depth = sharded_workload(args, world)
+    else:
+        wname, n, depth = args.workload, args.qubits, args.depth
+    n_cpu = n
+    while n_cpu > 20 and 2.2 * 16 * 2 ** n_cpu / 2 ** 30 > 0.8 * host_mem_available_gib():
+        n_cpu -= 1
+    n_cpu = min(n_cpu, 30)
+    circ, wl = build_workload(wname, n, depth)
+    circ_cpu = circ if n_cpu == n else build_workload(wname, n_cpu, depth)[0]
     budget = max(4.0, 170.0 / max(1, args.steps + args.warmup))
-    gps, desc, sec = time_cpu_path(circ, args.qubits, budget, steps=args.steps, warmup=args.warmup)
+    gps, desc, sec = time_cpu_path(circ_cpu, n_cpu, budget, steps=args.steps, warmup=args.warmup)
+    if n_cpu != n:
+        gps /= 2.0 ** (n - n_cpu)
+        desc += (f"; measured on the same generator at {n_cpu} qubits (a {n}-qubit complex128 state does not fit "
+                 f"this host) and divided by 2^{n - n_cpu}: every numpy gate pass is linear in the state size")
     line = {
         "impl": "reference", "metric": "gates/sec", "value": gps, "unit": "gates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
-        "config": {"workload": wl, "n_qubits": args.qubits},
+        "config": {"workload": wl, "n_qubits": n},
         "cpu_baseline": {"value": gps, "unit": "gates/s", "cores": 1, "kind": "port", "sample": desc},
         "e2e": {"value": gps, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -193,8 +231,7 @@ def run_b200(args):
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1:
-        from qaqarot_b200 import bench_sharded
-        return bench_sharded.run(args)
+        return run_sharded(args, world)
 
     n = args.qubits
     circ, wl = build_workload(args.workload, n, args.depth)
@@ -311,13 +348,141 @@ def run_b200(args):
     print(json.dumps(line), flush=True)
 
 
+def sharded_workload(args, world: int):
+    """BASELINE configs[3] / [4]: 33-qubit random layers on 2 and 4 GPUs, 36 qubits on 8 (depth 8)."""
+    if args.workload != "auto":
+        return args.workload, args.qubits, args.depth
+    return "layers", (36 if world >= 8 else 33), 8
+
+
+def run_sharded(args, world: int):
+    import random
+    import torch
+    import torch.distributed as dist
+    from qaqarot_b200 import ShardedB200Backend
+    rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    wname, n, depth = sharded_workload(args, world)
+    circ, wl = build_workload(wname, n, depth)
+    cfg = None
+    if args.tile_bits:
+        from qaqarot_b200.planner import PlanConfig
+        cfg = PlanConfig(a=args.tile_bits)
+    be = ShardedB200Backend(device=local, plan_config=cfg)
+    comp = be._compile(circ.ops, n, 0)
+    prog = comp.prefix
+    st = be._state(n)
+    n_local = st.n_local
+    st.set_profiling(True)
+
+    def step():
+        st.set_basis(0)
+        st.apply(prog)
+
+    def fence():
+        st.sync()
+        torch.cuda.synchronize(local)
+        dist.barrier()
+        torch.cuda.synchronize(local)
+
+    for _ in range(args.warmup):
+        step()
+    fence()
+    launches0, ex_ms0, ex_bytes0 = st.launch_count(), st.exchange_ms, st.exchange_bytes
+    st.profile = []
+    sampler = ClockSampler(local) if rank == 0 else None
+    time.sleep(0.3)
+    t0 = time.perf_counter()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(args.steps):
+        step()
+    fence()
+    stop.record()
+    stop.synchronize()
+    t1 = time.perf_counter()
+    ms = torch.tensor([start.elapsed_time(stop)], device=f"cuda:{local}", dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    clocks = sampler.stop(t0, t1) if sampler else None
+    launches = st.launch_count() - launches0
+    profile = st.profile
+    st.set_profiling(False)
+    sec_per_step = total_ms / 1e3 / args.steps
+    gates = comp.n_gates
+    ex = torch.tensor([st.exchange_ms - ex_ms0], device=f"cuda:{local}", dtype=torch.float64)
+    dist.all_reduce(ex, op=dist.ReduceOp.MAX)
+    ex_ms_step = float(ex.item()) / args.steps
+    ex_bytes_step = (st.exchange_bytes - ex_bytes0) / args.steps
+    norm2 = st.norm2()
+
+    # dominant kernel on this rank
+    peak, peak_src = measured_peak_gbs()
+    by_kind = {}
+    for kinds, mss in profile:
+        for k, m in zip(kinds, mss):
+            d = by_kind.setdefault(int(k), [0, 0.0])
+            d[0] += 1
+            d[1] += float(m)
+    dom = max(by_kind, key=lambda k: by_kind[k][1])
+    cnt, tot = by_kind[dom]
+    kind_names = {1: "k_mat", 2: "k_diag/k_phase", 3: "k_x", 4: "k_swapbits", 5: "k_involution", 16: "k_tile", 17: "k_scale"}
+    avg_ms = tot / cnt
+    alg_bytes = 32.0 * 2 ** n_local
+    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": kind_names.get(dom, str(dom)), "launches_timed": cnt, "avg_launch_ms": avg_ms,
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "share_of_step": tot / total_ms,
+                "per_gpu": True}
+    exchange = {"count_per_step": prog.n_exchanges, "ms_per_step": ex_ms_step,
+                "bytes_sent_per_gpu_per_step": ex_bytes_step,
+                "nvlink_gbs_per_direction": (ex_bytes_step / (ex_ms_step * 1e-3) / 1e9) if ex_ms_step > 0 else None,
+                "share_of_step": ex_ms_step / (sec_per_step * 1e3),
+                "note": "half a shard per exchange over NCCL send/recv through a 256 MiB bounce buffer, copy-back included"}
+
+    # end to end through the plugin API: plan, upload, run, sample 1000 shots, Counter back on the host
+    shots = 1000
+    circ_m = circ.copy(copy_backends=False).m[:]
+    random.seed(7)
+    be._compiled = None
+    fence()
+    t0 = time.perf_counter()
+    counts = circ_m.run(backend=be, shots=shots)
+    fence()
+    e2e_sec = time.perf_counter() - t0
+    ops_arr, n_ops, words, reals = prog.frozen()
+    e2e = {"value": gates / e2e_sec, "unit": "gates/s", "h2d_bytes_per_step": int(n_ops * 40 + words.nbytes + reals.nbytes
+                                                                                    + shots * n * 8),
+           "d2h_bytes_per_step": int(n * shots * 16), "ms_per_step": e2e_sec * 1e3, "steps": 1,
+           "note": f"Circuit.m[:].run(backend=ShardedB200Backend, shots={shots}) -> Counter; planning, program upload, "
+                   f"sharded sampling descent included; {len(counts)} distinct outcomes"}
+    be.close()
+    if rank == 0:
+        line = {
+            "metric": "gates/sec", "value": gates / sec_per_step, "unit": "gates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+            "config": {"workload": wl + f", sharded on the top {world.bit_length() - 1} index bits", "n_qubits": n,
+                       "n_local": n_local, "gates": gates, "passes": prog.n_passes - prog.n_exchanges,
+                       "state_bytes_per_gpu": int(16 * 2 ** n_local), "l2": "shard larger than L2 (no flush needed)"},
+            "amp_updates_per_s": gates * 2.0 ** n / sec_per_step,
+            "hbm_gbs": world * (prog.pass_bytes - 16.0 * 2 ** n_local * prog.n_exchanges) / sec_per_step / 1e9,
+            "roofline": roofline, "exchange": exchange, "cpu_baseline": None, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks, "check": {"norm2": norm2},
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="qft", choices=["qft", "layers"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "qft", "layers"])
     ap.add_argument("--qubits", type=int, default=30)
     ap.add_argument("--depth", type=int, default=20)
     ap.add_argument("--no-fusion", action="store_true")
@@ -326,6 +491,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 and args.workload == "auto":
+        args.workload = "qft"
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)

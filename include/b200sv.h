@@ -74,6 +74,9 @@ int b200_state_set_basis(b200_state* st, uint64_t index);                       
 int b200_state_upload(b200_state* st, const double* host, uint64_t offset, uint64_t count);   /* initial= */
 int b200_state_download(const b200_state* st, double* host, uint64_t offset, uint64_t count); /* returns   */
 int b200_state_copy(b200_state* dst, const b200_state* src);                    /* ctx.cache (:564-568)    */
+/* A state that is one shard of a larger register: `offset` carries the index bits above n_qubits (the shard
+   number shifted left by n_qubits).  Controls, phases and Pauli-Z signs on those qubits read them from here. */
+int b200_state_set_index_offset(b200_state* st, uint64_t offset);
 
 /* ---- unitary evolution (replaces _run_inner's gate loop, numpy_backend.py:545-570) -------------- */
 
@@ -105,6 +108,12 @@ int b200_first_above(b200_state* st, double eps, uint64_t* index, double* re, do
    the state.  out_bits[s] gets bit j set when qubit order[j] measured 1.  m <= 64.                     */
 int b200_sample(b200_state* st, const int32_t* order, int m, const double* uniforms, int n_shots,
                 uint64_t* out_bits);
+/* One level of that descent, for callers that combine partial sums themselves (a state sharded over several
+   GPUs adds the per-shard sums before comparing with the uniforms).  For every group g -- the amplitudes whose
+   index equals group_bits[g] on `fixed_mask` -- sums[2g] = sum |amp|^2 with bit `qubit` = 0 and sums[2g+1]
+   with bit = 1; qubit < 0: sums[2g] is the whole group.                                                   */
+int b200_cond_probs(b200_state* st, uint64_t fixed_mask, int qubit, const uint64_t* group_bits, int n_groups,
+                    double* sums);
 
 /* ---- Pauli expectation (replaces Expr.to_matrix + sparse_expectation, pauli.py:893-935,
         vqe.py:355-366).  One group = all terms sharing the same X/Y flip mask `xmask`:

@@ -23,9 +23,10 @@ def _bits(mask: int):
 
 
 class OracleState:
-    def __init__(self, n_qubits: int, device: int = 0):
+    def __init__(self, n_qubits: int, device: int = 0, index_offset: int = 0):
         self.n_qubits = n_qubits
         self.device = device
+        self.index_offset = index_offset       # shard number << n_qubits (qaqarot_b200/sharded.py)
         self.psi = np.zeros(1 << n_qubits, dtype=complex)
         self.psi[0] = 1.0
         self.launches = 0
@@ -108,7 +109,7 @@ class OracleState:
                 self.psi *= complex(reals[o.roff], reals[o.roff + 1])
             elif o.kind == OP_TILE:
                 from oracle.tile_interp import run_tile_pass
-                run_tile_pass(self.psi, n, words[o.woff:o.woff + o.wlen], reals)
+                run_tile_pass(self.psi, n, words[o.woff:o.woff + o.wlen], reals, self.index_offset)
             else:
                 raise ValueError(f"unknown op kind {o.kind}")
             self.launches += 1
@@ -176,13 +177,30 @@ class OracleState:
             out[s] = bits
         return out
 
+    def set_index_offset(self, offset):
+        self.index_offset = offset
+
+    def cond_probs(self, fixed_mask, qubit, group_bits):
+        prob = self.psi.real ** 2 + self.psi.imag ** 2
+        idx = np.arange(self.dim, dtype=np.int64)
+        out = np.zeros((len(group_bits), 2))
+        for g, gb in enumerate(group_bits):
+            sel = (idx & int(fixed_mask)) == int(gb)
+            if qubit < 0:
+                out[g, 0] = prob[sel].sum()
+            else:
+                bit = (idx >> qubit) & 1
+                out[g, 0] = prob[sel & (bit == 0)].sum()
+                out[g, 1] = prob[sel & (bit == 1)].sum()
+        return out
+
     def expect_group(self, xmask, zymasks, coeffs):
         idx = np.arange(self.dim, dtype=np.int64)
         w = np.zeros(self.dim, dtype=complex)
         for zy, c in zip(zymasks, coeffs):
             par = np.zeros(self.dim, dtype=np.int64)
             for b in _bits(int(zy)):
-                par ^= (idx >> b) & 1
+                par ^= ((idx | self.index_offset) >> b) & 1
             w += complex(c) * (1 - 2 * par)
         return complex(np.sum(np.conj(self.psi[idx ^ int(xmask)]) * self.psi * w))
 

@@ -4,11 +4,11 @@
 bundled host mirror), so ``Circuit(...).run(backend="b200")`` is a drop-in for ``run(backend="numpy")``.
 The CUDA library is loaded lazily, on the first run; there is no CPU fallback.
 """
-from .backend import B200Backend
+from .backend import B200Backend, ShardedB200Backend
 from .circuit import BackendRegistry, Circuit
 from .pauli import I, X, Y, Z
 from .register import register
 
-__all__ = ["B200Backend", "BackendRegistry", "Circuit", "X", "Y", "Z", "I", "register"]
+__all__ = ["B200Backend", "ShardedB200Backend", "BackendRegistry", "Circuit", "X", "Y", "Z", "I", "register"]
 
 register()

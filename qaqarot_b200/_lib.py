@@ -34,6 +34,7 @@ class Op(C.Structure):
 
 
 OP_MAT, OP_DIAG, OP_X, OP_SWAP, OP_PERMUTE, OP_TILE, OP_SCALE = 1, 2, 3, 4, 5, 16, 17
+OP_EXCHANGE = 32      # host-level: exchange index bit `target` (top local) with global bit `aux`; never sent to the C ABI
 
 _lib: Optional[C.CDLL] = None
 
@@ -64,6 +65,8 @@ _SIGNATURES = {
     "b200_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "b200_expect_group": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                     _P(C.c_double), _P(C.c_double)]),
+    "b200_cond_probs": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "b200_state_set_index_offset": (C.c_int, [C.c_void_p, C.c_uint64]),
     "b200_sync": (C.c_int, [C.c_void_p]),
     "b200_event_record": (C.c_int, [C.c_void_p, C.c_int]),
     "b200_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _P(C.c_double)]),

@@ -62,13 +62,25 @@ class RunContext:
 class _Compiled:
     """Lowered + planned form of gates[start:], cached on the backend between runs of the same circuit."""
 
-    def __init__(self, gates: Sequence, n_qubits: int, start: int, planner: Callable[[Sequence[Prim], int], Program]):
+    def __init__(self, gates: Sequence, n_qubits: int, start: int, planner: Callable[..., Program],
+                 initial_layout: Optional[Sequence[int]] = None):
         self.gates = tuple(gates)
         self.n_qubits = n_qubits
         self.start = start
+        self.initial_layout = list(initial_layout) if initial_layout is not None else None
         low = lower(self.gates[start:], n_qubits, start)
         self.n_gates = low.n_gates
         prims = low.prims
+        user_planner = planner
+        layout = [self.initial_layout]
+
+        def planner(seg, n):            # a sharded planner leaves wires where they are: thread the layout along
+            if getattr(user_planner, "threads_layout", False):
+                prog = user_planner(seg, n, layout[0])
+                layout[0] = list(prog.final_pos)
+                return prog
+            return user_planner(seg, n)
+
         k = low.first_nonunitary if low.first_nonunitary is not None else len(prims)
         self.prefix_prims = prims[:k]
         self.prefix = planner(self.prefix_prims, n_qubits)
@@ -88,8 +100,9 @@ class _Compiled:
             self.rest.append(planner(seg, n_qubits))
         self.terminal = bool(self.rest) and all(isinstance(r, Prim) and r.kind == "measure" for r in self.rest)
 
-    def matches(self, gates: Sequence, n_qubits: int, start: int) -> bool:
+    def matches(self, gates: Sequence, n_qubits: int, start: int, initial_layout=None) -> bool:
         return (n_qubits == self.n_qubits and start == self.start and len(gates) == len(self.gates)
+                and (list(initial_layout) if initial_layout is not None else None) == self.initial_layout
                 and all(a is b for a, b in zip(gates, self.gates)))
 
 
@@ -162,10 +175,10 @@ class B200Backend(_Base):
             self._work = self._state_factory(n_qubits, self.device)
         return self._work
 
-    def _compile(self, gates: Sequence, n_qubits: int, start: int) -> _Compiled:
+    def _compile(self, gates: Sequence, n_qubits: int, start: int, initial_layout=None) -> _Compiled:
         c = self._compiled
-        if c is None or not c.matches(gates, n_qubits, start):
-            c = self._compiled = _Compiled(gates, n_qubits, start, self._planner)
+        if c is None or not c.matches(gates, n_qubits, start, initial_layout):
+            c = self._compiled = _Compiled(gates, n_qubits, start, self._planner, initial_layout)
         return c
 
     def _download(self, st) -> np.ndarray:
@@ -181,7 +194,7 @@ class B200Backend(_Base):
         ctx = RunContext(n_qubits)
         cache, cache_idx = (self.cache, self.cache_idx) if use_backend_cache else (None, -1)
         start = cache_idx + 1 if cache is not None else 0
-        comp = self._compile(gates, n_qubits, start)
+        comp = self._compile(gates, n_qubits, start, getattr(cache, "layout", None) if cache is not None else None)
         st = self._state(n_qubits)
         ctx.device_state = st
         if cache is not None:
@@ -429,3 +442,41 @@ def _ignore_global_phase(st) -> None:
     if hit is not None:
         q = hit[1]
         st.scale(abs(q) / q)
+
+
+class ShardedB200Backend(B200Backend):
+    """The same backend with the register sharded over the ranks of a torch.distributed process group (one
+    process per GPU, launched with torchrun).  Every rank runs the same circuit and gets the same results:
+    statevectors are gathered (small registers), Counters and expectation values are identical everywhere --
+    seed Python's ``random`` identically on all ranks for shots.  See qaqarot_b200/sharded.py."""
+
+    def __init__(self, device: Optional[int] = None, plan_config=None, group=None, host_state_factory=None):
+        import os
+        import torch.distributed as dist
+        from .planner import DEFAULT, plan
+        from .sharded import ShardedState
+        if not dist.is_initialized():
+            raise RuntimeError("ShardedB200Backend needs torch.distributed.init_process_group() first")
+        world = dist.get_world_size(group)
+        g = world.bit_length() - 1
+        cfg = plan_config or DEFAULT
+        if device is None and host_state_factory is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+
+        def planner(prims, n, layout=None):
+            return plan(prims, n, cfg, n_local=n - g, initial_pos=layout)
+        planner.threads_layout = True
+
+        def factory(n, dev):
+            return ShardedState(n, device=dev, group=group, host_state_factory=host_state_factory)
+        super().__init__(device=device if device is not None else 0, fusion=True, state_factory=factory, planner=planner,
+                         plan_config=plan_config)
+        self.group = group
+        self._host_state_factory = host_state_factory
+
+    def copy(self) -> "ShardedB200Backend":
+        other = ShardedB200Backend(self.device, self.plan_config, self.group, self._host_state_factory)
+        if self.cache is not None:
+            other.cache = self.cache.clone()
+            other.cache_idx = self.cache_idx
+        return other

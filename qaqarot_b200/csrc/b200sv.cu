@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(kThreads) k_prob(const c128* __restrict__ amp,
   if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
 
-__global__ void __launch_bounds__(kThreads) k_expect(const c128* __restrict__ amp, uint64_t dim, uint64_t xmask,
+__global__ void __launch_bounds__(kThreads) k_expect(const c128* __restrict__ amp, uint64_t dim, uint64_t offset,
+                                                     uint64_t xmask,
                                                      int nt, const uint64_t* __restrict__ zy,
                                                      const double* __restrict__ cre, const double* __restrict__ cim,
                                                      double* __restrict__ partial) {
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(kThreads) k_expect(const c128* __restrict__ am
     const c128 b = xmask ? amp[i ^ xmask] : a;
     double wr = 0.0, wi = 0.0;
     for (int k = 0; k < nt; ++k) {
-      const bool neg = __popcll(i & s_zy[k]) & 1;
+      const bool neg = __popcll((i | offset) & s_zy[k]) & 1;
       wr += neg ? -s_re[k] : s_re[k];
       wi += neg ? -s_im[k] : s_im[k];
     }
@@ -306,6 +307,13 @@ int b200_state_destroy(b200_state* st) {
   for (cudaEvent_t e : st->user_events) if (e) cudaEventDestroy(e);
   if (st->stream) cudaStreamDestroy(st->stream);
   delete st;
+  return 0;
+}
+
+int b200_state_set_index_offset(b200_state* st, uint64_t offset) {
+  B200_REQUIRE(st != nullptr, "b200_state_set_index_offset: null state");
+  B200_REQUIRE((offset & (st->dim - 1)) == 0, "b200_state_set_index_offset: offset overlaps the state's own index bits");
+  st->index_offset = offset;
   return 0;
 }
 
@@ -649,7 +657,7 @@ int b200_expect_group(b200_state* st, uint64_t xmask, int n_terms, const uint64_
     B200_CUDA(cudaMemcpyAsync(st->d_reals + nt, cim + base, sizeof(double) * nt, cudaMemcpyHostToDevice, st->stream));
     const int blocks = reduce_blocks(st->dim);
     const size_t smem = (size_t)nt * (sizeof(uint64_t) + 2 * sizeof(double));
-    k_expect<<<blocks, kThreads, smem, st->stream>>>(st->amp, st->dim, xmask, nt, st->d_words, st->d_reals,
+    k_expect<<<blocks, kThreads, smem, st->stream>>>(st->amp, st->dim, st->index_offset, xmask, nt, st->d_words, st->d_reals,
                                                     st->d_reals + nt, st->d_partial);
     st->launches++;
     B200_CUDA(cudaGetLastError());

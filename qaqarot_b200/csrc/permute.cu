@@ -36,43 +36,69 @@ __device__ __forceinline__ uint32_t inv_swz(uint32_t l) {
   return l ^ ((l >> 3) & 7u) ^ ((l >> 6) & 7u) ^ ((l >> 9) & 7u);
 }
 
-__global__ void __launch_bounds__(kInvThreads) k_involution(c128* __restrict__ amp, uint64_t n_tiles, InvDesc d) {
+constexpr int kInvEPT = (1 << kInvMaxA) / kInvThreads;     // amplitudes per thread per tile (at most)
+
+__global__ void __launch_bounds__(kInvThreads) k_involution(c128* __restrict__ amp, uint64_t n_tiles,
+                                                            const __grid_constant__ InvDesc d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  c128* sa = reinterpret_cast<c128*>(smem_raw);
-  c128* sb = sa + (1u << d.a);
+  unsigned char* const sa = smem_raw;
+  unsigned char* const sb = smem_raw + (16u << d.a);
   const uint32_t n_local = 1u << d.a;
+  // Everything that depends only on the local index is computed once per thread: where local index l sits in
+  // the index space (off), its shared-memory slot when written, and the slot its *source* element was written to.
+  uint64_t off[kInvEPT];
+  uint32_t wslot[kInvEPT], rslot[kInvEPT];
+#pragma unroll
+  for (int k = 0; k < kInvEPT; ++k) {
+    const uint32_t l = threadIdx.x + k * kInvThreads;
+    uint64_t o = 0;
+    uint32_t ls = 0;
+#pragma unroll
+    for (int i = 0; i < kInvMaxA; ++i)
+      if (i < d.a) {
+        o |= (uint64_t)((l >> i) & 1u) << d.tile[i];
+        ls |= ((l >> i) & 1u) << d.src_local[i];          // involution: source bit <-> destination bit
+      }
+    off[k] = o;
+    wslot[k] = inv_swz(l) << 4;
+    rslot[k] = inv_swz(ls) << 4;
+  }
   for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
     uint64_t t2 = t;
+#pragma unroll 1
     for (int i = 0; i < d.n_outer; ++i) {
       const uint64_t bu = (t >> d.ou[i]) & 1ull, bv = (t >> d.ov[i]) & 1ull;
       if (bu != bv) t2 ^= (1ull << d.ou[i]) | (1ull << d.ov[i]);
     }
     if (t2 < t || (t2 == t && d.inner_identity)) continue;         // CTA-uniform
     uint64_t base = t, base2 = t2;
-    for (int i = 0; i < d.a; ++i) {
-      base = insert_zero(base, d.tile[i]);
-      base2 = insert_zero(base2, d.tile[i]);
-    }
-    const bool two = t2 != t;
-    for (uint32_t l = threadIdx.x; l < n_local; l += kInvThreads) {
-      uint64_t off = 0;
-      for (int i = 0; i < d.a; ++i) off |= (uint64_t)((l >> i) & 1u) << d.tile[i];
-      const uint32_t s = inv_swz(l);
-      sa[s] = amp[base + off];
-      if (two) sb[s] = amp[base2 + off];
-    }
-    __syncthreads();
-    for (uint32_t l = threadIdx.x; l < n_local; l += kInvThreads) {
-      uint64_t off = 0;
-      uint32_t ls = 0;
-      for (int i = 0; i < d.a; ++i) {
-        off |= (uint64_t)((l >> i) & 1u) << d.tile[i];
-        ls |= ((l >> i) & 1u) << d.src_local[i];          // involution: source bit <-> destination bit
+#pragma unroll
+    for (int i = 0; i < kInvMaxA; ++i)
+      if (i < d.a) {
+        base = insert_zero(base, d.tile[i]);
+        base2 = insert_zero(base2, d.tile[i]);
       }
-      const uint32_t s = inv_swz(ls);
-      amp[base2 + off] = sa[s];
-      if (two) amp[base + off] = sb[s];
-    }
+    const bool two = t2 != t;
+    c128 x[kInvEPT], y[kInvEPT];
+#pragma unroll
+    for (int k = 0; k < kInvEPT; ++k)
+      if (threadIdx.x + k * kInvThreads < n_local) {
+        x[k] = __ldcg(amp + base + off[k]);
+        if (two) y[k] = __ldcg(amp + base2 + off[k]);
+      }
+#pragma unroll
+    for (int k = 0; k < kInvEPT; ++k)
+      if (threadIdx.x + k * kInvThreads < n_local) {
+        *reinterpret_cast<c128*>(sa + wslot[k]) = x[k];
+        if (two) *reinterpret_cast<c128*>(sb + wslot[k]) = y[k];
+      }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kInvEPT; ++k)
+      if (threadIdx.x + k * kInvThreads < n_local) {
+        __stcg(amp + base2 + off[k], *reinterpret_cast<const c128*>(sa + rslot[k]));
+        if (two) __stcg(amp + base + off[k], *reinterpret_cast<const c128*>(sb + rslot[k]));
+      }
     __syncthreads();
   }
 }

@@ -85,6 +85,58 @@ struct DeviceBuf {
 
 using namespace b200;
 
+// One level of the descent: for every group g (amplitudes whose index has exactly the bits group_bits[g] among
+// `fixed_mask`), S0 = sum |amp|^2 over the group with bit `qubit` = 0 and S1 with bit = 1 (qubit < 0: S0 is the
+// whole group, S1 = 0).  sums[2g], sums[2g+1].  All masks are over this state's own n index bits.
+static int cond_probs(b200_state* st, uint64_t fixed_mask, int qubit, const uint64_t* group_bits, int n_groups,
+                      double* sums) {
+  const int max_blocks = kSMs * 16;
+  const uint64_t tbit = qubit >= 0 ? 1ull << qubit : 0ull;
+  DeviceBuf d_bits, d_partial, d_out;
+  B200_CUDA(cudaMalloc(&d_bits.p, sizeof(uint64_t) * n_groups));
+  B200_CUDA(cudaMalloc(&d_partial.p, sizeof(double) * 2 * ((size_t)n_groups + (size_t)max_blocks)));
+  B200_CUDA(cudaMalloc(&d_out.p, sizeof(double) * 2 * n_groups));
+  FreeRuns fr;
+  fr.n = 0;
+  int free_bits = 0;
+  for (int b = 0; b < st->n;) {
+    if ((fixed_mask | tbit) >> b & 1) { ++b; continue; }
+    int e = b;
+    while (e < st->n && !((fixed_mask | tbit) >> e & 1)) ++e;
+    fr.start[fr.n] = (unsigned char)b;
+    fr.len[fr.n] = (unsigned char)(e - b);
+    ++fr.n;
+    free_bits += e - b;
+    b = e;
+  }
+  const uint64_t count = 1ull << free_bits;
+  uint64_t want = (count + (uint64_t)kSampThreads * 4 - 1) / ((uint64_t)kSampThreads * 4);
+  int bx = (int)std::min<uint64_t>(want, (uint64_t)std::max(1, max_blocks / n_groups));
+  if (bx < 1) bx = 1;
+  B200_CUDA(cudaMemcpyAsync(d_bits.p, group_bits, sizeof(uint64_t) * n_groups, cudaMemcpyHostToDevice, st->stream));
+  k_cond_prob<<<n_groups * bx, kSampThreads, 0, st->stream>>>(st->amp, count, fr, (const uint64_t*)d_bits.p, tbit, bx,
+                                                             (double*)d_partial.p);
+  B200_CUDA(cudaGetLastError());
+  k_group_finish<<<(n_groups + 127) / 128, 128, 0, st->stream>>>((const double*)d_partial.p, n_groups, bx,
+                                                                 (double*)d_out.p);
+  B200_CUDA(cudaGetLastError());
+  st->launches += 2;
+  B200_CUDA(cudaMemcpyAsync(sums, d_out.p, sizeof(double) * 2 * n_groups, cudaMemcpyDeviceToHost, st->stream));
+  B200_CUDA(cudaStreamSynchronize(st->stream));
+  return 0;
+}
+
+extern "C" int b200_cond_probs(b200_state* st, uint64_t fixed_mask, int qubit, const uint64_t* group_bits,
+                               int n_groups, double* sums) {
+  B200_REQUIRE(st != nullptr && group_bits != nullptr && sums != nullptr, "b200_cond_probs: null argument");
+  B200_REQUIRE(n_groups > 0, "b200_cond_probs: no groups");
+  B200_REQUIRE(qubit < st->n, "b200_cond_probs: qubit out of range");
+  B200_REQUIRE((fixed_mask & ~(st->dim - 1)) == 0, "b200_cond_probs: fixed mask out of range");
+  B200_REQUIRE(qubit < 0 || !((fixed_mask >> qubit) & 1), "b200_cond_probs: qubit is already fixed");
+  B200_CUDA(cudaSetDevice(st->device));
+  return cond_probs(st, fixed_mask, qubit, group_bits, n_groups, sums);
+}
+
 extern "C" int b200_sample(b200_state* st, const int32_t* order, int m, const double* uniforms, int n_shots,
                            uint64_t* out_bits) {
   B200_REQUIRE(st != nullptr && out_bits != nullptr, "b200_sample: null argument");
@@ -95,13 +147,6 @@ extern "C" int b200_sample(b200_state* st, const int32_t* order, int m, const do
   std::fill(out_bits, out_bits + n_shots, 0ull);
   if (m == 0 || n_shots == 0) return 0;
   B200_CUDA(cudaSetDevice(st->device));
-
-  const int max_blocks = kSMs * 16;
-  const size_t max_groups = (size_t)n_shots;
-  DeviceBuf d_bits, d_partial, d_out;
-  B200_CUDA(cudaMalloc(&d_bits.p, sizeof(uint64_t) * max_groups));
-  B200_CUDA(cudaMalloc(&d_partial.p, sizeof(double) * 2 * (max_groups + (size_t)max_blocks)));
-  B200_CUDA(cudaMalloc(&d_out.p, sizeof(double) * 2 * max_groups));
 
   std::vector<uint64_t> prefix(n_shots, 0ull);        // outcomes so far, as index bits
   std::vector<int> idx(n_shots), group_of(n_shots);
@@ -130,36 +175,8 @@ extern "C" int b200_sample(b200_state* st, const int32_t* order, int m, const do
       group_of[s] = (int)group_bits.size() - 1;
     }
     const int n_groups = (int)group_bits.size();
-    // free bits = everything not fixed and not the current qubit
-    FreeRuns fr;
-    fr.n = 0;
-    int free_bits = 0;
-    for (int b = 0; b < st->n;) {
-      if ((fixed_mask | tbit) >> b & 1) { ++b; continue; }
-      int e = b;
-      while (e < st->n && !((fixed_mask | tbit) >> e & 1)) ++e;
-      fr.start[fr.n] = (unsigned char)b;
-      fr.len[fr.n] = (unsigned char)(e - b);
-      ++fr.n;
-      free_bits += e - b;
-      b = e;
-    }
-    const uint64_t count = 1ull << free_bits;
-    uint64_t want = (count + (uint64_t)kSampThreads * 4 - 1) / ((uint64_t)kSampThreads * 4);
-    int bx = (int)std::min<uint64_t>(want, (uint64_t)std::max(1, max_blocks / n_groups));
-    if (bx < 1) bx = 1;
-    B200_CUDA(cudaMemcpyAsync(d_bits.p, group_bits.data(), sizeof(uint64_t) * n_groups, cudaMemcpyHostToDevice,
-                              st->stream));
-    k_cond_prob<<<n_groups * bx, kSampThreads, 0, st->stream>>>(st->amp, count, fr, (const uint64_t*)d_bits.p, tbit, bx,
-                                                               (double*)d_partial.p);
-    B200_CUDA(cudaGetLastError());
-    k_group_finish<<<(n_groups + 127) / 128, 128, 0, st->stream>>>((const double*)d_partial.p, n_groups, bx,
-                                                                   (double*)d_out.p);
-    B200_CUDA(cudaGetLastError());
-    st->launches += 2;
     sums.resize(2 * (size_t)n_groups);
-    B200_CUDA(cudaMemcpyAsync(sums.data(), d_out.p, sizeof(double) * 2 * n_groups, cudaMemcpyDeviceToHost, st->stream));
-    B200_CUDA(cudaStreamSynchronize(st->stream));
+    if (cond_probs(st, fixed_mask, q, group_bits.data(), n_groups, sums.data())) return 1;
     for (int s = 0; s < n_shots; ++s) {
       const int g = group_of[s];
       const double s0 = sums[2 * (size_t)g], s1 = sums[2 * (size_t)g + 1];

@@ -225,6 +225,7 @@ constexpr int kMaxRounds = 8;
 constexpr int kSpreadTabs = 5;     // 6 bits of the tile number each: up to 30 non-tile index bits
 
 constexpr int kMaxPayload = 3072;  // float64 payload of one pass kept in shared memory (planner.MAX_PAYLOAD)
+constexpr int kMaxFanWords = 1024; // directory + records of the pass's fans (planner keeps a pass below this)
 // record (one uint4): x = target kind | j<<4 | diag kind<<8 | (reg_mask != 0)<<12 | fan<<16 | fixed mask bits 32..39<<24
 //                     y = thread mask | reg mask<<16    z = target payload | diag payload<<16 (complex units, relative)
 //                     w = fixed mask bits 0..31
@@ -242,6 +243,7 @@ struct TileSmem {
   uint64_t spread[kSpreadTabs][64];
   uint4 rec[kMaxGates + 1];
   double pay[kMaxPayload];         // the pass's matrices, phases and fan tables
+  uint64_t fanw[kMaxFanWords];     // fan directory and records (entry counts, payload offsets, fixed-bit masks)
   RoundHdr rh[kMaxRounds];
   uint32_t thr[kMaxRounds][1 << (A - 4)];   // per round, per thread: local index bits | swizzled byte offset / 16 << 16
   uint32_t round_off[kMaxRounds];
@@ -279,6 +281,7 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
     }
   }
   for (uint32_t i = tid; i < pay_len; i += NT) S.pay[i] = reals[pay_lo + i];
+  for (uint32_t i = dir_off + tid; i < rounds_off; i += NT) S.fanw[i - dir_off] = desc[i];
   for (uint32_t idx = tid; idx < kSpreadTabs * 64; idx += NT) {
     uint64_t x = (uint64_t)(idx & 63u) << (6 * (idx >> 6));
     for (int i = 0; i < A; ++i) x = insert_zero(x, byte_of(tb_lo, tb_hi, i));
@@ -357,13 +360,13 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
 
     // per-tile fixed-bit products of the fans, while the copies are in flight (one warp per fan)
     for (int f = (int)warp; f < n_fans; f += (NT >> 5)) {
-      const uint32_t off = (uint32_t)desc[dir_off + f];
-      const uint64_t rec = desc[off];
+      const uint32_t off = (uint32_t)S.fanw[f] - dir_off;
+      const uint64_t rec = S.fanw[off];
       const int ne = (int)(rec & 0xFFFFFFFFu);
       const double2* __restrict__ w = reinterpret_cast<const double2*>(S.pay + ((uint32_t)(rec >> 32) - pay_lo));
       c128 p = make_double2(1.0, 0.0);
       for (int e = (int)lane; e < ne; e += 32) {
-        const uint64_t m = desc[off + 1 + e];
+        const uint64_t m = S.fanw[off + 1 + e];
         if ((fixedidx & m) == m) p = cmul(p, w[1 + e]);
       }
 #pragma unroll
@@ -497,6 +500,8 @@ int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_d
   const uint64_t dir_off = h_desc[3] & 0xFFFFFFFFu, rounds_off = h_desc[3] >> 32;
   B200_REQUIRE(dir_off + (uint64_t)n_fans <= (uint64_t)wlen && rounds_off <= (uint64_t)wlen,
                "TILE descriptor: offsets out of range");
+  B200_REQUIRE(rounds_off >= dir_off && rounds_off - dir_off <= (uint64_t)kMaxFanWords,
+               "TILE descriptor: fan records too long");
   B200_REQUIRE((h_desc[4] >> 32) <= (uint64_t)kMaxPayload && (h_desc[4] & 0xFFFFFFFFu) + (h_desc[4] >> 32) <= n_reals,
                "TILE descriptor: payload range too long or outside the reals pool");
   uint64_t pos = rounds_off, gates = 0;

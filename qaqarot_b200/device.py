@@ -148,6 +148,18 @@ class DeviceState:
     def sync(self) -> None:
         _lib.check(self._lib.b200_sync(self._h))
 
+    # -- shards (qaqarot_b200/sharded.py) -----------------------------------------------------------
+    def set_index_offset(self, offset: int) -> None:
+        _lib.check(self._lib.b200_state_set_index_offset(self._h, offset))
+
+    def cond_probs(self, fixed_mask: int, qubit: int, group_bits: np.ndarray) -> np.ndarray:
+        """(n_groups, 2): sum |amp|^2 of every group with bit `qubit` = 0 / 1 (qubit < 0: whole group, 0)."""
+        gb = np.ascontiguousarray(group_bits, dtype=np.uint64)
+        out = np.zeros((gb.size, 2), dtype=np.float64)
+        _lib.check(self._lib.b200_cond_probs(self._h, fixed_mask, qubit, gb.ctypes.data_as(C.c_void_p), gb.size,
+                                             out.ctypes.data_as(C.c_void_p)))
+        return out
+
     # -- timing (bench.py / profiling) ------------------------------------------------------------
     def event_record(self, slot: int) -> None:
         _lib.check(self._lib.b200_event_record(self._h, slot))

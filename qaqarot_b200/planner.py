@@ -35,6 +35,7 @@ T_NONE, T_MATC, T_MATR, T_X = 0, 1, 2, 3          # target stage of a tile gate 
 D_NONE, D_FANT, D_FAN, D_PHASE = 0, 1, 2, 3         # diagonal stage (fan without / with register table, phase)
 MAX_GATES = 160          # per pass (record slots in csrc/tile.cu)
 MAX_PAYLOAD = 3072       # float64 payload of one pass (shared-memory copy in csrc/tile.cu)
+MAX_FAN_WORDS = 1024     # fan directory + records of one pass (shared-memory copy in csrc/tile.cu)
 MAX_FANS = 64            # per pass (shared-memory slots in csrc/tile.cu)
 
 
@@ -74,7 +75,7 @@ class Item:
         if self.kind in ("mat", "x"):
             self.nd = frozenset((self.t,))
             self.dg = frozenset(self.ctrls)
-        elif self.kind == "swap":
+        elif self.kind in ("swap", "perm", "exchange"):
             self.nd = frozenset((self.t, self.aux))
             self.dg = frozenset()
         elif self.kind == "phase":
@@ -89,8 +90,8 @@ class Item:
             return f"<fan t{self.t} {sorted(self.entries)}>"
         if self.kind == "phase":
             return f"<phase {list(self.bits)}>"
-        if self.kind == "swap":
-            return f"<swap {self.t},{self.aux}>"
+        if self.kind in ("swap", "perm", "exchange"):
+            return f"<{self.kind} {self.t},{self.aux}>"
         return f"<{self.kind} t{self.t} c{list(self.ctrls)}>"
 
 
@@ -128,12 +129,19 @@ class Normalized:
         self.items: List[Item] = []
         self.n_prims = 0
         self.n_relabelled = 0                 # swap gates absorbed into the wire -> index-bit map
+        self.n_exchanges = 0                  # global <-> local index-bit exchanges (sharded states)
         self.final_pos: List[int] = []        # wire -> index bit at the end of the segment
 
 
 def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = True,
-              relabel_swaps: bool = True) -> Normalized:
+              relabel_swaps: bool = True, n_local: Optional[int] = None,
+              initial_pos: Optional[Sequence[int]] = None) -> Normalized:
+    """`n_local` < n: the state is sharded on its top n - n_local index bits (one shard per GPU).  A gate that is
+    non-diagonal on a wire living on such a *global* bit first brings the wire home: the global bit is exchanged
+    with the top local bit (an `exchange` item: half of every shard crosses NVLink), after a local transposition
+    (`perm`) has parked there the local wire whose next non-diagonal use is farthest away (Belady)."""
     out = Normalized()
+    n_local = n if n_local is None else n_local
     items = out.items
     pending: List[Optional[np.ndarray]] = [None] * n
     pending_count = [0] * n
@@ -232,13 +240,55 @@ def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = 
         else:
             push(Item("mat", t=q, m=m, n_prims=cnt), last_touch[q])
 
-    pos = list(range(n))                 # wire -> index bit its data lives on (swap gates only relabel)
-    for p in prims:
+    pos = list(initial_pos) if initial_pos is not None else list(range(n))   # wire -> index bit of its data
+    wire_at = [0] * n
+    for w_, p_ in enumerate(pos):
+        wire_at[p_] = w_
+    uses: List[List[int]] = [[] for _ in range(n)]      # per wire: prims that are non-diagonal on it
+    if n_local < n:
+        for i, p in enumerate(prims):
+            if p.kind in ("mat", "x") and not (p.kind == "mat" and _is_diag(_as_matrix(p))):
+                uses[p.target].append(i)
+    use_ptr = [0] * n
+
+    def move(a: int, b: int):
+        """Exchange the contents (wire, pending gate) of index bits a and b."""
+        wa, wb = wire_at[a], wire_at[b]
+        wire_at[a], wire_at[b] = wb, wa
+        pos[wa], pos[wb] = b, a
+        pending[a], pending[b] = pending[b], pending[a]
+        pending_count[a], pending_count[b] = pending_count[b], pending_count[a]
+
+    def bring_home(gpos: int, now: int) -> int:
+        """Make the wire on global bit `gpos` local; returns its new index bit."""
+        top = n_local - 1
+        best, best_next = top, -1
+        for q in range(n_local):
+            w = wire_at[q]
+            while use_ptr[w] < len(uses[w]) and uses[w][use_ptr[w]] <= now:
+                use_ptr[w] += 1
+            nxt = uses[w][use_ptr[w]] if use_ptr[w] < len(uses[w]) else len(prims) + 1
+            if nxt > best_next or (nxt == best_next and q == top):
+                best, best_next = q, nxt
+        # a pending non-diagonal 2x2 must be applied while its wire is still local
+        for q in (best, top):
+            if pending[q] is not None and not _is_diag(pending[q]):
+                flush(q)
+        if best != top:
+            push(Item("perm", t=best, aux=top, n_prims=0))
+            move(best, top)
+        push(Item("exchange", t=top, aux=gpos, n_prims=0))
+        move(top, gpos)
+        out.n_exchanges += 1
+        return top
+
+    for i_prim, p in enumerate(prims):
         out.n_prims += 1
         if p.kind == "swap":
             a, b = p.target, p.aux
             if relabel_swaps:
                 pos[a], pos[b] = pos[b], pos[a]
+                wire_at[pos[a]], wire_at[pos[b]] = a, b
                 out.n_relabelled += 1
                 continue
             pending[a], pending[b] = pending[b], pending[a]
@@ -246,6 +296,8 @@ def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = 
             push(Item("swap", t=a, aux=b))
             continue
         tgt = pos[p.target]
+        if tgt >= n_local and p.kind in ("mat", "x") and not (p.kind == "mat" and _is_diag(_as_matrix(p))):
+            tgt = bring_home(tgt, i_prim)
         ctrls = tuple(pos[cq] for cq in p.controls)
         if not ctrls and fuse_1q:
             g = _as_matrix(p)
@@ -392,6 +444,7 @@ def build_pass(remaining: List[Item], n: int, a: int, r: int, c: int, cfg: PlanC
     n_fans = 0
     n_gates = 0
     payload = 0
+    fan_words = 0
     limit = min(len(remaining), cfg.scan_limit)
     for _ in range(cfg.max_rounds):
         reg: List[int] = []
@@ -402,10 +455,11 @@ def build_pass(remaining: List[Item], n: int, a: int, r: int, c: int, cfg: PlanC
             if done[idx]:
                 continue
             it = remaining[idx]
-            ok = it.kind != "swap" and not _conflict(it, skipped_nd, skipped_dg)
+            ok = it.kind not in ("swap", "perm", "exchange") and not _conflict(it, skipped_nd, skipped_dg)
             pay = _payload(it, a, r)
+            fw = 3 + len(it.entries) if it.kind == "fan" else (1 if it.kind == "phase" else 0)
             if ok and ((it.kind == "fan" and n_fans >= MAX_FANS - 1) or n_gates + 2 >= MAX_GATES - 1
-                       or payload + pay > MAX_PAYLOAD - 64):
+                       or payload + pay > MAX_PAYLOAD - 64 or fan_words + fw > MAX_FAN_WORDS - 8):
                 ok = False
             if ok and it.nd:
                 t = it.t
@@ -424,6 +478,7 @@ def build_pass(remaining: List[Item], n: int, a: int, r: int, c: int, cfg: PlanC
                 n_fans += it.kind == "fan"
                 n_gates += 2 if it.kind == "fan" else 1
                 payload += pay
+                fan_words += fw
             else:
                 skipped_nd |= it.nd
                 skipped_dg |= it.dg
@@ -613,6 +668,7 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int) -> None:
     body: List[int] = []
     pay_len = len(prog._reals) - pay_lo
     assert pay_len <= MAX_PAYLOAD and sum(len(g) // 3 for _, g in encoded_rounds) <= MAX_GATES
+    assert n_fans + sum(len(rec) for rec in fan_records) <= MAX_FAN_WORDS
     base = 5 + n_fans
     for rec in fan_records:
         directory.append(base + len(body))
@@ -649,34 +705,61 @@ def _emit_single(prog: Program, it: Item, n: int) -> None:
     prog.n_prims += it.n_prims
 
 
-def plan(prims: Sequence[Prim], n_qubits: int, cfg: PlanConfig = DEFAULT) -> Program:
-    """Primitives of one unitary segment -> op program."""
+def plan(prims: Sequence[Prim], n_qubits: int, cfg: PlanConfig = DEFAULT, n_local: Optional[int] = None,
+         initial_pos: Optional[Sequence[int]] = None) -> Program:
+    """Primitives of one unitary segment -> op program.
+
+    Single GPU (n_local None): the program leaves every wire on its own index bit (relabelled swaps are paid back
+    by at most two PERMUTE passes at the end).  Sharded (n_local < n_qubits): index bits >= n_local are the shard
+    number; the program contains EXCHANGE ops for the host layer to run over NVLink, starts from `initial_pos`
+    and ends in the layout `program.final_pos` (wire -> index bit), which is *not* restored."""
     n = n_qubits
+    sharded = n_local is not None
+    nl = n_local if sharded else n
     prog = Program()
+    prog.initial_pos = list(initial_pos) if initial_pos is not None else list(range(n))
+    prog.final_pos = list(prog.initial_pos)
     if not prims:
         return prog
-    norm = normalize(prims, n)
-    if n < cfg.min_qubits:
+    norm = normalize(prims, n, n_local=nl, initial_pos=initial_pos)
+    prog.final_pos = list(norm.final_pos)
+    if not sharded and n < cfg.min_qubits:
         for it in norm.items:
             _emit_single(prog, it, n)
         _emit_restore(prog, norm, n)
+        prog.final_pos = list(range(n))
         return prog
-    a = min(cfg.a, n)
+    a = min(cfg.a, nl)
     if a not in cfg.kernel_tiles:
         a = max(t for t in cfg.kernel_tiles if t <= a)
     r = min(cfg.r, a)
     c = min(cfg.c, a)
     remaining = list(norm.items)
     while remaining:
-        if remaining[0].kind == "swap":
+        head = remaining[0]
+        if head.kind == "swap":
             _emit_single(prog, remaining.pop(0), n)
             continue
-        ps, rest = build_pass(remaining, n, a, r, c, cfg)
+        if head.kind == "perm":
+            remaining.pop(0)
+            woff = prog.add_words([min(head.t, head.aux) | (max(head.t, head.aux) << 8)])
+            prog.add_op(_lib.OP_PERMUTE, woff=woff, wlen=1, nbytes=16.0 * 2 ** nl)
+            continue
+        if head.kind == "exchange":
+            remaining.pop(0)
+            prog.add_op(_lib.OP_EXCHANGE, head.t, aux=head.aux, nbytes=16.0 * 2 ** nl)
+            prog.n_exchanges += 1
+            continue
+        ps, rest = build_pass(remaining, nl, a, r, c, cfg)
         if not ps.rounds:                                   # cannot happen: the head item always fits
             raise RuntimeError(f"planner made no progress at {remaining[0]}")
-        encode_pass(prog, ps, n, r, c)
+        encode_pass(prog, ps, nl, r, c)
         remaining = rest
-    _emit_restore(prog, norm, n)
+    if sharded:
+        prog.n_prims += norm.n_relabelled
+    else:
+        _emit_restore(prog, norm, n)
+        prog.final_pos = list(range(n))
     return prog
 
 

@@ -21,6 +21,9 @@ class Program:
         self.pass_bytes = 0.0     # algorithmic bytes moved, summed over passes (set by the planner)
         self._frozen = None
         self._bytes: List[float] = []   # algorithmic bytes per op (read + write of the amplitudes it touches)
+        self.n_exchanges = 0            # OP_EXCHANGE ops (run by the host layer of a sharded state over NVLink)
+        self.initial_pos: List[int] = []   # wire -> index bit the program assumes / leaves (planner.plan)
+        self.final_pos: List[int] = []
 
     # -- building -------------------------------------------------------------------------------
     def add_reals(self, values: Sequence[complex]) -> int:
@@ -80,6 +83,27 @@ class Program:
 
     def __len__(self):
         return len(self._ops)
+
+    def segments(self):
+        """Split at the host-level EXCHANGE ops: yields sub-programs (sharing this program's payload pools) and
+        (top local bit, global bit) tuples, in order."""
+        out, cur = [], None
+        for op, nbytes in zip(self._ops, self._bytes):
+            if op[0] == _lib.OP_EXCHANGE:
+                if cur is not None:
+                    out.append(cur)
+                    cur = None
+                out.append((op[1], op[2]))
+                continue
+            if cur is None:
+                cur = Program()
+                cur._words, cur._reals = self._words, self._reals
+            cur._ops.append(op)
+            cur._bytes.append(nbytes)
+            cur.n_passes += 1
+        if cur is not None:
+            out.append(cur)
+        return out
 
 
 def unfused_program(prims: Sequence[Prim], n_qubits: int = 0) -> Program:

@@ -1,0 +1,400 @@
+"""A statevector sharded over the GPUs of one box: one process per GPU, ``torch.distributed`` for the plumbing.
+
+The reference has no distributed code at all; this is new.  The 2^n amplitudes are split on
+the top ``log2(P)`` index bits: rank r holds the amplitudes whose *global* bits equal r, as an ordinary
+``n_local = n - log2(P)``-qubit device state whose ``index_offset`` tells the kernels which shard it is
+(include/b200sv.h: b200_state_set_index_offset).  Consequences:
+
+* gates whose non-diagonal target lives on a local bit run with no communication; controls, phases, fans and
+  Pauli-Z signs on global bits cost nothing either (per-shard constants);
+* a non-diagonal gate on a global wire makes the planner emit an EXCHANGE op (planner.normalize/bring_home):
+  the global bit swaps places with the top local bit, i.e. every rank trades one *contiguous* half of its shard
+  with the partner rank whose shard number differs in that bit -- ``isend``/``irecv`` over NCCL (NVLink), through
+  a bounded bounce buffer because a 36-qubit shard (128 GiB) leaves no room for a second copy;
+* the wire -> index-bit layout is tracked (``layout``) and *not* undone after a program: measurement, sampling
+  and expectation values translate wire numbers instead, and only ``download`` (small registers) un-permutes;
+* scalars (norms, conditional probabilities, expectation partial sums) are all-reduced.
+
+The local state is pluggable so that the same logic runs on CPU under ``gloo`` with the numpy program
+interpreter standing in for the device (tests/test_sharded.py); on a GPU box it is a ``DeviceState`` wrapping a
+torch CUDA tensor, so that NCCL can address the amplitudes directly.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .program import Program
+
+
+def _torch():
+    import torch
+    import torch.distributed as dist
+    return torch, dist
+
+
+class _CudaLocal:
+    """n_local-qubit DeviceState living in a torch CUDA tensor (so torch.distributed can send / receive it)."""
+
+    def __init__(self, n_local: int, index_offset: int, device: int):
+        torch, _ = _torch()
+        from .device import DeviceState
+        torch.cuda.set_device(device)
+        self.tensor = torch.zeros(2 << n_local, dtype=torch.float64, device=f"cuda:{device}")
+        self.state = DeviceState(n_local, device, wrap_ptr=self.tensor.data_ptr())
+        self.state.set_index_offset(index_offset)
+        self.device = device
+
+    def buffer(self):
+        return self.tensor
+
+    def before_comm(self):
+        self.state.sync()                      # kernels run on the state's own stream
+
+    def after_comm(self):
+        torch, _ = _torch()
+        torch.cuda.synchronize(self.device)
+
+    def close(self):
+        self.state.close()
+        self.tensor = None
+
+
+class _HostLocal:
+    """CPU stand-in: the numpy interpreter of the op program (test infrastructure injects the class)."""
+
+    def __init__(self, state):
+        torch, _ = _torch()
+        self.state = state
+        self.tensor = torch.from_numpy(state.psi.view(np.float64))
+
+    def buffer(self):
+        return self.tensor
+
+    def before_comm(self):
+        pass
+
+    def after_comm(self):
+        pass
+
+    def close(self):
+        pass
+
+
+class ShardedState:
+    """Same method surface as ``device.DeviceState``, in *wire* coordinates, collective across the process group.
+    Every rank must make the same calls in the same order."""
+
+    BOUNCE_AMPS = 1 << 24           # 256 MiB bounce buffer for exchanges
+
+    def __init__(self, n_qubits: int, device: Optional[int] = None, group=None, host_state_factory=None):
+        torch, dist = _torch()
+        if not dist.is_initialized():
+            raise RuntimeError("ShardedState needs an initialised torch.distributed process group")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        g = self.world.bit_length() - 1
+        if 1 << g != self.world:
+            raise ValueError(f"world size {self.world} is not a power of two")
+        if n_qubits - g < 1:
+            raise ValueError(f"{n_qubits} qubits cannot be sharded over {self.world} ranks")
+        self.n_qubits = n_qubits
+        self.n_global = g
+        self.n_local = n_qubits - g
+        self.layout: List[int] = list(range(n_qubits))       # wire -> index bit
+        offset = self.rank << self.n_local
+        if host_state_factory is not None:
+            self.local = _HostLocal(host_state_factory(self.n_local, offset))
+        else:
+            self.local = _CudaLocal(self.n_local, offset, 0 if device is None else device)
+        self.device = device
+        self._bounce = None
+        self.exchange_bytes = 0          # bytes this rank has sent (= received) in exchanges
+        self.exchange_ms = 0.0           # wall time spent in exchanges (synchronised), for reporting
+        self.n_exchanges = 0
+        self.profile = None              # list of (kinds, ms) per executed segment while profiling is on
+
+    def set_profiling(self, on: bool) -> None:
+        self.st.set_profiling(on)
+        self.profile = [] if on else None
+
+    # -- helpers ----------------------------------------------------------------------------------
+    @property
+    def st(self):
+        return self.local.state
+
+    @property
+    def dim(self) -> int:
+        return 1 << self.n_qubits
+
+    def _allreduce(self, values: np.ndarray) -> np.ndarray:
+        torch, dist = _torch()
+        t = torch.from_numpy(np.ascontiguousarray(values, dtype=np.float64).copy())
+        if dist.get_backend(self.group) == "nccl":
+            t = t.cuda(self.local.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
+    def _my_bit(self, index_bit: int) -> int:
+        return (self.rank >> (index_bit - self.n_local)) & 1
+
+    def _phys_index(self, wire_index: int) -> int:
+        p = 0
+        for w in range(self.n_qubits):
+            if (wire_index >> w) & 1:
+                p |= 1 << self.layout[w]
+        return p
+
+    def _wire_at(self) -> List[int]:
+        inv = [0] * self.n_qubits
+        for w, p in enumerate(self.layout):
+            inv[p] = w
+        return inv
+
+    # -- lifetime / contents ----------------------------------------------------------------------
+    def close(self) -> None:
+        if self.local is not None:
+            self.local.close()
+            self.local = None
+        self._bounce = None
+
+    def set_basis(self, index: int = 0) -> None:
+        self.layout = list(range(self.n_qubits))
+        owner, local_index = index >> self.n_local, index & ((1 << self.n_local) - 1)
+        if owner == self.rank:
+            self.st.set_basis(local_index)
+        else:
+            self.st.set_basis(0)
+            self.st.scale(0.0)
+
+    def upload(self, vec: np.ndarray, offset: int = 0) -> None:
+        """`vec`: the whole register in wire order (every rank passes the same array)."""
+        assert offset == 0 and vec.size == self.dim
+        self.layout = list(range(self.n_qubits))
+        lo = self.rank << self.n_local
+        self.st.upload(np.ascontiguousarray(vec[lo:lo + (1 << self.n_local)], dtype=np.complex128))
+
+    def download_shard(self) -> np.ndarray:
+        """This rank's amplitudes in physical order (index bit k of the local index = index bit k)."""
+        return self.st.download()
+
+    def download(self, offset: int = 0, count: Optional[int] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """The whole register in wire order, on every rank.  Small registers only (2^n amplitudes on the host)."""
+        torch, dist = _torch()
+        if self.n_qubits > 30:
+            raise ValueError("download() of a sharded register above 30 qubits: use download_shard() and `layout`")
+        mine = torch.from_numpy(self.st.download().view(np.float64).copy())
+        nccl = dist.get_backend(self.group) == "nccl"
+        if nccl:
+            mine = mine.cuda(self.local.device)
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(parts, mine, group=self.group)
+        phys = np.concatenate([p.cpu().numpy() for p in parts]).view(np.complex128)
+        if self.layout != list(range(self.n_qubits)):
+            idx = np.arange(self.dim, dtype=np.int64)
+            src = np.zeros(self.dim, dtype=np.int64)
+            for w, p in enumerate(self.layout):
+                src |= ((idx >> w) & 1) << p
+            phys = phys[src]
+        res = phys if offset == 0 and count is None else phys[offset:offset + (count or self.dim - offset)]
+        if out is not None:
+            out[:] = res
+            return out
+        return np.ascontiguousarray(res)
+
+    def copy_from(self, other: "ShardedState") -> None:
+        self.st.copy_from(other.st)
+        self.layout = list(other.layout)
+
+    def clone(self) -> "ShardedState":
+        """A second register of the same size (the caller must know it fits: snapshots for mid-circuit
+        measurement with several shots, save_cache)."""
+        factory = None
+        if isinstance(self.local, _HostLocal):
+            proto = self.local.state
+            factory = lambda nl, off: type(proto)(nl, 0, off)
+        c = ShardedState(self.n_qubits, self.device, self.group, factory)
+        c.copy_from(self)
+        return c
+
+    # -- evolution --------------------------------------------------------------------------------
+    def apply(self, program: Program) -> None:
+        if len(program) == 0 and not program.final_pos:
+            return
+        if program.initial_pos and list(program.initial_pos) != self.layout:
+            raise ValueError("program was planned for a different wire layout than the state is in")
+        for seg in program.segments():
+            if isinstance(seg, Program):
+                self.st.apply(seg)
+                if self.profile is not None:
+                    ms, kinds = self.st.last_op_times()
+                    self.profile.append((kinds.copy(), ms.copy()))
+            else:
+                self.exchange(*seg)
+        if program.final_pos:
+            self.layout = list(program.final_pos)
+
+    def exchange(self, top: int, gpos: int) -> None:
+        """Swap index bit `top` (must be the top local bit) with global bit `gpos`: trade the half of the shard
+        whose top bit differs from this rank's bit `gpos` with the partner rank.  Layout is the caller's job."""
+        torch, dist = _torch()
+        import time
+        assert top == self.n_local - 1 and gpos >= self.n_local
+        partner = self.rank ^ (1 << (gpos - self.n_local))
+        half = 1 << (self.n_local - 1)                          # amplitudes
+        start = half if self._my_bit(gpos) == 0 else 0
+        buf = self.local.buffer()                               # float64 view, 2 doubles per amplitude
+        chunk = min(half, self.BOUNCE_AMPS)
+        if self._bounce is None or self._bounce.numel() < 2 * chunk:
+            self._bounce = torch.empty(2 * chunk, dtype=torch.float64, device=buf.device)
+        self.local.before_comm()
+        t0 = time.perf_counter()
+        for off in range(0, half, chunk):
+            region = buf[2 * (start + off): 2 * (start + off + chunk)]
+            tmp = self._bounce[:2 * chunk]
+            ops = [dist.P2POp(dist.isend, region, partner, self.group), dist.P2POp(dist.irecv, tmp, partner, self.group)]
+            if self.rank > partner:
+                ops.reverse()
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            region.copy_(tmp)
+        self.local.after_comm()
+        self.exchange_ms += (time.perf_counter() - t0) * 1e3
+        self.exchange_bytes += 16 * half
+        self.n_exchanges += 1
+
+    def _make_local(self, wires: Sequence[int]) -> None:
+        """Bring every wire in `wires` onto a local index bit (used by measurement / X-Y expectation values)."""
+        need = [w for w in wires if self.layout[w] >= self.n_local]
+        if not need:
+            return
+        keep = set(self.layout[w] for w in wires)
+        top = self.n_local - 1
+        for w in need:
+            inv = self._wire_at()
+            if top in keep:                                      # park an uninvolved local wire on the top bit first
+                victim = max(p for p in range(self.n_local) if p not in keep)
+                prog = Program()
+                woff = prog.add_words([victim | (top << 8)])
+                prog.add_op(_lib.OP_PERMUTE, woff=woff, wlen=1)
+                self.st.apply(prog)
+                a, b = inv[victim], inv[top]
+                self.layout[a], self.layout[b] = top, victim
+                keep.discard(top)
+                keep.add(victim)
+                inv = self._wire_at()
+            gpos = self.layout[w]
+            self.exchange(top, gpos)
+            evicted = inv[top]
+            self.layout[w], self.layout[evicted] = top, gpos
+            keep.add(top)
+
+    # -- measurement ------------------------------------------------------------------------------
+    def norm2(self) -> float:
+        return float(self._allreduce(np.array([self.st.norm2()]))[0])
+
+    def prob_zero(self, target: int) -> float:
+        p = self.layout[target]
+        if p < self.n_local:
+            mine = self.st.prob_zero(p)
+        else:
+            mine = self.st.norm2() if self._my_bit(p) == 0 else 0.0
+        return float(self._allreduce(np.array([mine]))[0])
+
+    def collapse(self, target: int, outcome: int, p: float, reset: bool = False) -> None:
+        """Never changes the layout (the programs that follow were planned for it)."""
+        torch, dist = _torch()
+        pb = self.layout[target]
+        if pb < self.n_local:
+            self.st.collapse(pb, outcome, p, reset=reset)
+            return
+        keep = self._my_bit(pb) == outcome
+        self.st.scale(1.0 / math.sqrt(p) if keep else 0.0)
+        if reset and outcome == 1:
+            # move the surviving |1> shards onto their |0> partners, whole shards at a time
+            partner = self.rank ^ (1 << (pb - self.n_local))
+            buf = self.local.buffer()
+            self.local.before_comm()
+            chunk = 2 * self.BOUNCE_AMPS
+            for off in range(0, buf.numel(), chunk):
+                part = buf[off:off + chunk]
+                if keep:
+                    dist.send(part, partner, group=self.group)
+                else:
+                    dist.recv(part, partner, group=self.group)
+            self.local.after_comm()
+            if keep:
+                self.st.scale(0.0)
+
+    def scale(self, z: complex) -> None:
+        self.st.scale(z)
+
+    def first_above(self, eps: float) -> Optional[Tuple[int, complex]]:
+        vec = self.download()
+        hit = np.nonzero(np.abs(vec) > eps)[0]
+        if hit.size == 0:
+            return None
+        return int(hit[0]), complex(vec[hit[0]])
+
+    def sample(self, order: Sequence[int], uniforms: np.ndarray) -> np.ndarray:
+        """The descent of csrc/sample.cu with the per-level sums added over the shards."""
+        order = [int(q) for q in order]
+        m = len(order)
+        uniforms = np.asarray(uniforms, dtype=np.float64).reshape(-1, max(1, m))
+        n_shots = uniforms.shape[0]
+        out = np.zeros(n_shots, dtype=np.uint64)
+        prefix = np.zeros(n_shots, dtype=np.uint64)           # outcomes so far, as physical index bits
+        fixed_mask = 0
+        lmask = (1 << self.n_local) - 1
+        mine = self.rank << self.n_local
+        for j, wire in enumerate(order):
+            pb = self.layout[wire]
+            tbit = 1 << pb
+            if fixed_mask & tbit:
+                ones = (prefix & np.uint64(tbit)) != 0
+                p0 = np.where(ones, 0.0, 1.0)
+                bit = ~(uniforms[:, j] < p0)
+                out |= bit.astype(np.uint64) << np.uint64(j)
+                continue
+            groups, inverse = np.unique(prefix, return_inverse=True)
+            sums = np.zeros((groups.size, 2))
+            gmask = fixed_mask & ~lmask
+            here = [i for i, gb in enumerate(groups) if (int(gb) & ~lmask) == (mine & gmask)]
+            if here:
+                local_bits = np.array([int(groups[i]) & lmask for i in here], dtype=np.uint64)
+                if pb < self.n_local:
+                    part = self.st.cond_probs(fixed_mask & lmask, pb, local_bits)
+                    sums[here] = part
+                else:
+                    part = self.st.cond_probs(fixed_mask & lmask, -1, local_bits)
+                    sums[here, self._my_bit(pb)] = part[:, 0]
+            sums = self._allreduce(sums.reshape(-1)).reshape(-1, 2)
+            p0 = sums[inverse, 0] / (sums[inverse, 0] + sums[inverse, 1])
+            bit = ~(uniforms[:, j] < p0)
+            out |= bit.astype(np.uint64) << np.uint64(j)
+            prefix |= np.where(bit, np.uint64(tbit), np.uint64(0))
+            fixed_mask |= tbit
+        return out
+
+    def expect_group(self, xmask: int, zymasks: Sequence[int], coeffs: Sequence[complex]) -> complex:
+        wires = [w for w in range(self.n_qubits) if (xmask >> w) & 1]
+        self._make_local(wires)                                 # X / Y pair amplitudes inside one shard only
+        def phys(mask: int) -> int:
+            return self._phys_index(int(mask))
+        val = self.st.expect_group(phys(xmask), [phys(z) for z in zymasks], coeffs)
+        tot = self._allreduce(np.array([val.real, val.imag]))
+        return complex(tot[0], tot[1])
+
+    # -- bookkeeping ------------------------------------------------------------------------------
+    def launch_count(self) -> int:
+        return self.st.launch_count()
+
+    def last_program_ms(self) -> float:
+        return self.st.last_program_ms()
+
+    def sync(self) -> None:
+        self.st.sync()
