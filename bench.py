@@ -99,6 +99,8 @@ def build_workload(name: str, n: int, depth: int):
         return W.qft(n), f"{n}-qubit QFT of basis state 123456789, complex128, gate fusion on"
     if name == "layers":
         return W.random_layers(n, depth), f"{n}-qubit random H/RZ/CX layers depth {depth}, complex128, gate fusion on"
+    if name == "qaoa":
+        return W.qaoa_maxcut(n)[0], f"{n}-qubit QAOA MaxCut on C_n(1, n/2), p=4, complex128, gate fusion on"
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -482,7 +484,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "qft", "layers"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "qft", "layers", "qaoa"])
     ap.add_argument("--qubits", type=int, default=30)
     ap.add_argument("--depth", type=int, default=20)
     ap.add_argument("--no-fusion", action="store_true")

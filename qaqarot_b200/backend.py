@@ -213,8 +213,10 @@ class B200Backend(_Base):
             ctx.samples = [{} for _ in range(shots)]
             return ctx
 
+        # a snapshot is only needed to re-run measurements shot by shot (or to keep as the cache): terminal
+        # measurements are sampled without collapsing, and a second copy of a large register may not even fit
         snap = None
-        if shots > 1 or save_cache:
+        if (shots > 1 and not comp.terminal) or save_cache:
             snap = st.clone()
         if save_cache:
             self._clear_cache()

@@ -124,6 +124,32 @@ def _as_matrix(p: Prim) -> np.ndarray:
     return _XM
 
 
+def fold_conjugated_phases(prims: Sequence[Prim]) -> List[Prim]:
+    """CX(c,t) . D(t) . CX(c,t) with D = diag(d0, d1) is diagonal: D(t) . diag_c(1, r) . CD_{c->t}(1, r^-2), r = d1/d0
+    (the amplitude picks up d0 * r^(t xor c)).  This is how blueqat's time evolution emits exp(-i a Z.Z)
+    (pauli.py:596-630 -> cx, rz, cx; also the rzz fallback, gate.py:1142-1147): a QAOA cost layer then needs no
+    non-diagonal target at all and rides along with whatever pass comes next."""
+    out: List[Prim] = []
+    i, n = 0, len(prims)
+    while i < n:
+        p = prims[i]
+        if (i + 2 < n and p.kind == "x" and len(p.controls) == 1):
+            d, q = prims[i + 1], prims[i + 2]
+            if (d.kind == "diag" and not d.controls and d.target == p.target and q.kind == "x"
+                    and q.controls == p.controls and q.target == p.target and abs(complex(d.data[0])) > 0.5):
+                d0, d1 = complex(d.data[0]), complex(d.data[1])
+                r = d1 / d0
+                c = p.controls[0]
+                out.append(d)
+                out.append(Prim("diag", c, (), np.array([1.0, r]), op_index=p.op_index))
+                out.append(Prim("diag", p.target, (c,), np.array([1.0, 1.0 / (r * r)]), op_index=q.op_index))
+                i += 3
+                continue
+        out.append(p)
+        i += 1
+    return out
+
+
 class Normalized:
     def __init__(self):
         self.items: List[Item] = []
@@ -240,6 +266,8 @@ def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = 
         else:
             push(Item("mat", t=q, m=m, n_prims=cnt), last_touch[q])
 
+    n_in = len(prims)
+    prims = fold_conjugated_phases(prims)
     pos = list(initial_pos) if initial_pos is not None else list(range(n))   # wire -> index bit of its data
     wire_at = [0] * n
     for w_, p_ in enumerate(pos):
