@@ -364,6 +364,7 @@ def run_sharded(args, world: int):
     from qaqarot_b200 import ShardedB200Backend
     rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    os.environ["NCCL_DEBUG"] = os.environ.get("B200_NCCL_DEBUG", "WARN")     # keep NCCL's banner off stdout
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     wname, n, depth = sharded_workload(args, world)
     circ, wl = build_workload(wname, n, depth)
@@ -375,6 +376,7 @@ def run_sharded(args, world: int):
     comp = be._compile(circ.ops, n, 0)
     prog = comp.prefix
     st = be._state(n)
+    st.use_p2p = not args.nccl_exchange
     n_local = st.n_local
     st.set_profiling(True)
 
@@ -441,7 +443,9 @@ def run_sharded(args, world: int):
                 "bytes_sent_per_gpu_per_step": ex_bytes_step,
                 "nvlink_gbs_per_direction": (ex_bytes_step / (ex_ms_step * 1e-3) / 1e9) if ex_ms_step > 0 else None,
                 "share_of_step": ex_ms_step / (sec_per_step * 1e3),
-                "note": "half a shard per exchange over NCCL send/recv through a 256 MiB bounce buffer, copy-back included"}
+                "note": ("half a shard per exchange, swapped in place by k_peer_swap over CUDA-IPC peer memory (NVLink), "
+                         "fences included" if st.use_p2p else
+                         "half a shard per exchange over NCCL send/recv through a 256 MiB bounce buffer, copy-back included")}
 
     # end to end through the plugin API: plan, upload, run, sample 1000 shots, Counter back on the host
     shots = 1000
@@ -491,6 +495,7 @@ def main():
     ap.add_argument("--tile-bits", type=int, default=0, help="override the planner's tile size (log2 amplitudes)")
     ap.add_argument("--detail", default="", help="write per-op device times of the timed steps to this JSON file")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--nccl-exchange", action="store_true", help="sharded runs: exchange through NCCL send/recv instead of the peer-to-peer kernel")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -123,6 +123,17 @@ int b200_expect_group(b200_state* st, uint64_t xmask, int n_terms, const uint64_
 
 int b200_sync(b200_state* st);
 
+/* ---- peer-to-peer exchange for states sharded over several GPUs, one process each (no reference
+        counterpart: blueqat has no distributed path) ----------------------------------------- */
+
+/* CUDA IPC handle (64 bytes) of a state created by b200_state_create; the partner process maps it. */
+int b200_state_ipc_export(const b200_state* st, unsigned char* handle64);
+int b200_ipc_open(int device, const unsigned char* handle64, void** peer_amps);
+int b200_ipc_close(void* peer_amps);
+/* amp[start + i] <-> peer_amps[peer_start + i] for i < count, by loads / stores over NVLink, synchronous.
+   The two partners call it on disjoint ranges; the caller fences both processes before and after. */
+int b200_peer_swap(b200_state* st, void* peer_amps, uint64_t start, uint64_t peer_start, uint64_t count);
+
 /* ---- measurement support for bench.py / profiling ------------------------------------------------ */
 
 /* Record CUDA event `slot` (0..15) on the state's stream; elapsed device time between two recorded slots. */

@@ -162,4 +162,71 @@ int launch_permute(b200_state* st, const uint64_t* pairs, int n_pairs) {
   return 0;
 }
 
+// ---- direct peer-to-peer exchange of a contiguous range (sharded states, one process per GPU) ------------------
+// mine[i] <-> peer[i] for i in [0, count): `peer` is the partner GPU's shard mapped through CUDA IPC, reached
+// over NVLink by plain loads and stores.  The two partners call this on disjoint halves of the range, so every
+// element is swapped exactly once and both NVLink directions carry the same traffic; nothing is staged.
+__global__ void __launch_bounds__(256) k_peer_swap(c128* __restrict__ mine, c128* __restrict__ peer, uint64_t count) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // four independent 16-byte transfers in flight per thread in each direction
+  for (; i + 3 * stride < count; i += 4 * stride) {
+    c128 x[4], y[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) y[k] = __ldcg(peer + i + k * stride);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x[k] = __ldcg(mine + i + k * stride);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) __stcg(peer + i + k * stride, x[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) __stcg(mine + i + k * stride, y[k]);
+  }
+  for (; i < count; i += stride) {
+    const c128 y = __ldcg(peer + i), x = __ldcg(mine + i);
+    __stcg(peer + i, x);
+    __stcg(mine + i, y);
+  }
+}
+
 }  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_state_ipc_export(const b200_state* st, unsigned char* handle64) {
+  B200_REQUIRE(st != nullptr && handle64 != nullptr, "b200_state_ipc_export: null argument");
+  B200_REQUIRE(st->owns, "b200_state_ipc_export: only states created by b200_state_create can be exported");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  B200_CUDA(cudaSetDevice(st->device));
+  cudaIpcMemHandle_t h;
+  B200_CUDA(cudaIpcGetMemHandle(&h, st->amp));
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+
+extern "C" int b200_ipc_open(int device, const unsigned char* handle64, void** peer_amps) {
+  B200_REQUIRE(handle64 != nullptr && peer_amps != nullptr, "b200_ipc_open: null argument");
+  B200_CUDA(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  B200_CUDA(cudaIpcOpenMemHandle(peer_amps, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+
+extern "C" int b200_ipc_close(void* peer_amps) {
+  if (peer_amps) B200_CUDA(cudaIpcCloseMemHandle(peer_amps));
+  return 0;
+}
+
+extern "C" int b200_peer_swap(b200_state* st, void* peer_amps, uint64_t start, uint64_t peer_start, uint64_t count) {
+  B200_REQUIRE(st != nullptr && peer_amps != nullptr, "b200_peer_swap: null argument");
+  B200_REQUIRE(start <= st->dim && count <= st->dim - start && peer_start <= st->dim && count <= st->dim - peer_start,
+               "b200_peer_swap: range exceeds the state");
+  if (count == 0) return 0;
+  B200_CUDA(cudaSetDevice(st->device));
+  const unsigned grid = kSMs * 8;
+  k_peer_swap<<<grid, 256, 0, st->stream>>>(st->amp + start, static_cast<c128*>(peer_amps) + peer_start, count);
+  st->launches++;
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaStreamSynchronize(st->stream));
+  return 0;
+}

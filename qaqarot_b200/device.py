@@ -152,6 +152,25 @@ class DeviceState:
     def set_index_offset(self, offset: int) -> None:
         _lib.check(self._lib.b200_state_set_index_offset(self._h, offset))
 
+    def ipc_export(self) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        _lib.check(self._lib.b200_state_ipc_export(self._h, buf))
+        return bytes(buf)
+
+    def ipc_open(self, handle: bytes) -> int:
+        """Map a partner process's state (its ipc_export()) into this process; returns the device pointer."""
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        _lib.check(self._lib.b200_ipc_open(self.device, buf, C.byref(p)))
+        return p.value
+
+    def ipc_close(self, peer_ptr: int) -> None:
+        _lib.check(self._lib.b200_ipc_close(C.c_void_p(peer_ptr)))
+
+    def peer_swap(self, peer_ptr: int, start: int, peer_start: int, count: int) -> None:
+        """amp[start + i] <-> peer[peer_start + i], i < count (synchronous)."""
+        _lib.check(self._lib.b200_peer_swap(self._h, C.c_void_p(peer_ptr), start, peer_start, count))
+
     def cond_probs(self, fixed_mask: int, qubit: int, group_bits: np.ndarray) -> np.ndarray:
         """(n_groups, 2): sum |amp|^2 of every group with bit `qubit` = 0 / 1 (qubit < 0: whole group, 0)."""
         gb = np.ascontiguousarray(group_bits, dtype=np.uint64)

@@ -36,17 +36,25 @@ def _torch():
     return torch, dist
 
 
+class _DevicePointer:
+    """Exposes device memory owned by the C library to torch (``__cuda_array_interface__``), zero copy."""
+
+    def __init__(self, ptr: int, n_doubles: int):
+        self.__cuda_array_interface__ = {"shape": (n_doubles,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
 class _CudaLocal:
-    """n_local-qubit DeviceState living in a torch CUDA tensor (so torch.distributed can send / receive it)."""
+    """n_local-qubit DeviceState (memory owned by libb200sv) plus a torch view of it for torch.distributed."""
 
     def __init__(self, n_local: int, index_offset: int, device: int):
         torch, _ = _torch()
         from .device import DeviceState
         torch.cuda.set_device(device)
-        self.tensor = torch.zeros(2 << n_local, dtype=torch.float64, device=f"cuda:{device}")
-        self.state = DeviceState(n_local, device, wrap_ptr=self.tensor.data_ptr())
+        self.state = DeviceState(n_local, device)
         self.state.set_index_offset(index_offset)
+        self.tensor = torch.as_tensor(_DevicePointer(self.state.device_ptr, 2 << n_local), device=f"cuda:{device}")
         self.device = device
+        self.peers = {}                        # partner rank -> mapped device pointer of its shard
 
     def buffer(self):
         return self.tensor
@@ -59,8 +67,14 @@ class _CudaLocal:
         torch.cuda.synchronize(self.device)
 
     def close(self):
-        self.state.close()
+        for p in self.peers.values():
+            try:
+                self.state.ipc_close(p)
+            except Exception:
+                pass
+        self.peers = {}
         self.tensor = None
+        self.state.close()
 
 
 class _HostLocal:
@@ -117,6 +131,7 @@ class ShardedState:
         self.exchange_ms = 0.0           # wall time spent in exchanges (synchronised), for reporting
         self.n_exchanges = 0
         self.profile = None              # list of (kinds, ms) per executed segment while profiling is on
+        self.use_p2p = True              # exchanges by the in-place peer-to-peer kernel (GPUs only)
 
     def set_profiling(self, on: bool) -> None:
         self.st.set_profiling(on)
@@ -240,19 +255,56 @@ class ShardedState:
 
     def exchange(self, top: int, gpos: int) -> None:
         """Swap index bit `top` (must be the top local bit) with global bit `gpos`: trade the half of the shard
-        whose top bit differs from this rank's bit `gpos` with the partner rank.  Layout is the caller's job."""
+        whose top bit differs from this rank's bit `gpos` with the partner rank.  Layout is the caller's job.
+
+        On GPUs the two partners swap in place over NVLink with one kernel each (csrc/permute.cu k_peer_swap on
+        the partner's shard mapped through CUDA IPC), each taking one half of the range; ``use_p2p = False`` or a
+        host stand-in falls back to NCCL / gloo send-recv through a bounce buffer."""
         torch, dist = _torch()
         import time
         assert top == self.n_local - 1 and gpos >= self.n_local
         partner = self.rank ^ (1 << (gpos - self.n_local))
         half = 1 << (self.n_local - 1)                          # amplitudes
+        self.local.before_comm()
+        dist.barrier(group=self.group)                          # both shards are quiescent
+        t0 = time.perf_counter()
+        if self.use_p2p and isinstance(self.local, _CudaLocal):
+            peer = self._peer_pointer(partner)
+            # element (top = 1, global bit 0, rest x) <-> (top = 0, global bit 1, rest x): on the rank whose bit is 0
+            # that is mine[half + x] <-> peer[x], on its partner mine[x] <-> peer[half + x]
+            mine0 = half if self._my_bit(gpos) == 0 else 0
+            peer0 = half - mine0
+            if half == 1:
+                lo, cnt = 0, (1 if self.rank < partner else 0)
+            else:
+                lo, cnt = (0 if self.rank < partner else half // 2), half // 2     # each partner moves half the range
+            self.st.peer_swap(peer, mine0 + lo, peer0 + lo, cnt)
+        else:
+            self._exchange_sendrecv(partner, half, gpos)
+        self.local.after_comm()
+        dist.barrier(group=self.group)
+        self.exchange_ms += (time.perf_counter() - t0) * 1e3
+        self.exchange_bytes += 16 * half
+        self.n_exchanges += 1
+
+    def _peer_pointer(self, partner: int) -> int:
+        torch, dist = _torch()
+        if partner not in self.local.peers:
+            # every rank publishes its handle once; all ranks take part in the gather
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self.st.ipc_export(), group=self.group)
+            for r, h in enumerate(handles):
+                if r != self.rank and r not in self.local.peers and bin(r ^ self.rank).count("1") == 1:
+                    self.local.peers[r] = self.st.ipc_open(h)
+        return self.local.peers[partner]
+
+    def _exchange_sendrecv(self, partner: int, half: int, gpos: int) -> None:
+        torch, dist = _torch()
         start = half if self._my_bit(gpos) == 0 else 0
         buf = self.local.buffer()                               # float64 view, 2 doubles per amplitude
         chunk = min(half, self.BOUNCE_AMPS)
         if self._bounce is None or self._bounce.numel() < 2 * chunk:
             self._bounce = torch.empty(2 * chunk, dtype=torch.float64, device=buf.device)
-        self.local.before_comm()
-        t0 = time.perf_counter()
         for off in range(0, half, chunk):
             region = buf[2 * (start + off): 2 * (start + off + chunk)]
             tmp = self._bounce[:2 * chunk]
@@ -262,10 +314,6 @@ class ShardedState:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
             region.copy_(tmp)
-        self.local.after_comm()
-        self.exchange_ms += (time.perf_counter() - t0) * 1e3
-        self.exchange_bytes += 16 * half
-        self.n_exchanges += 1
 
     def _make_local(self, wires: Sequence[int]) -> None:
         """Bring every wire in `wires` onto a local index bit (used by measurement / X-Y expectation values)."""
