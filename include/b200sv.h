@@ -130,9 +130,11 @@ int b200_sync(b200_state* st);
 int b200_state_ipc_export(const b200_state* st, unsigned char* handle64);
 int b200_ipc_open(int device, const unsigned char* handle64, void** peer_amps);
 int b200_ipc_close(void* peer_amps);
-/* amp[start + i] <-> peer_amps[peer_start + i] for i < count, by loads / stores over NVLink, synchronous.
-   The two partners call it on disjoint ranges; the caller fences both processes before and after. */
-int b200_peer_swap(b200_state* st, void* peer_amps, uint64_t start, uint64_t peer_start, uint64_t count);
+/* Exchange local index bit `lbit` with the global bit in which the two shards differ (`my_bit` = this shard's
+   value of it): for the pairs i in [start, start + count) of the 2^(n-1) index patterns without bit lbit,
+   amp[i with lbit = 1 - my_bit] <-> peer_amps[i with lbit = my_bit], by loads / stores over NVLink, synchronous.
+   The two partners call it on disjoint pair ranges; the caller fences both processes before and after. */
+int b200_peer_swap(b200_state* st, void* peer_amps, int lbit, int my_bit, uint64_t start, uint64_t count);
 
 /* ---- measurement support for bench.py / profiling ------------------------------------------------ */
 

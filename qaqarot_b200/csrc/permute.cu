@@ -162,29 +162,37 @@ int launch_permute(b200_state* st, const uint64_t* pairs, int n_pairs) {
   return 0;
 }
 
-// ---- direct peer-to-peer exchange of a contiguous range (sharded states, one process per GPU) ------------------
-// mine[i] <-> peer[i] for i in [0, count): `peer` is the partner GPU's shard mapped through CUDA IPC, reached
-// over NVLink by plain loads and stores.  The two partners call this on disjoint halves of the range, so every
-// element is swapped exactly once and both NVLink directions carry the same traffic; nothing is staged.
-__global__ void __launch_bounds__(256) k_peer_swap(c128* __restrict__ mine, c128* __restrict__ peer, uint64_t count) {
+// ---- direct peer-to-peer exchange of one index bit (sharded states, one process per GPU) ----------------------
+// Exchanging local index bit `lbit` with a global bit means: this rank (global bit b) trades its amplitudes whose
+// bit lbit is 1-b with the partner's amplitudes whose bit lbit is b, all other bits equal.  `peer` is the partner
+// GPU's shard mapped through CUDA IPC, reached over NVLink by plain 16-byte loads and stores (runs of 2^lbit
+// amplitudes are contiguous on both sides).  The two partners call this on disjoint halves of the pair range, so
+// every pair is swapped exactly once and both NVLink directions carry the same traffic; nothing is staged.
+__global__ void __launch_bounds__(256) k_peer_swap(c128* __restrict__ mine, c128* __restrict__ peer, uint64_t start,
+                                                   uint64_t count, int lbit, int my_bit) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t mbit = (uint64_t)(1 - my_bit) << lbit, pbit = (uint64_t)my_bit << lbit;
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   // four independent 16-byte transfers in flight per thread in each direction
   for (; i + 3 * stride < count; i += 4 * stride) {
     c128 x[4], y[4];
+    uint64_t k0[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) y[k] = __ldcg(peer + i + k * stride);
+    for (int k = 0; k < 4; ++k) k0[k] = insert_zero(start + i + k * stride, lbit);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) x[k] = __ldcg(mine + i + k * stride);
+    for (int k = 0; k < 4; ++k) y[k] = __ldcg(peer + (k0[k] | pbit));
 #pragma unroll
-    for (int k = 0; k < 4; ++k) __stcg(peer + i + k * stride, x[k]);
+    for (int k = 0; k < 4; ++k) x[k] = __ldcg(mine + (k0[k] | mbit));
 #pragma unroll
-    for (int k = 0; k < 4; ++k) __stcg(mine + i + k * stride, y[k]);
+    for (int k = 0; k < 4; ++k) __stcg(peer + (k0[k] | pbit), x[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) __stcg(mine + (k0[k] | mbit), y[k]);
   }
   for (; i < count; i += stride) {
-    const c128 y = __ldcg(peer + i), x = __ldcg(mine + i);
-    __stcg(peer + i, x);
-    __stcg(mine + i, y);
+    const uint64_t k0 = insert_zero(start + i, lbit);
+    const c128 y = __ldcg(peer + (k0 | pbit)), x = __ldcg(mine + (k0 | mbit));
+    __stcg(peer + (k0 | pbit), x);
+    __stcg(mine + (k0 | mbit), y);
   }
 }
 
@@ -217,14 +225,14 @@ extern "C" int b200_ipc_close(void* peer_amps) {
   return 0;
 }
 
-extern "C" int b200_peer_swap(b200_state* st, void* peer_amps, uint64_t start, uint64_t peer_start, uint64_t count) {
+extern "C" int b200_peer_swap(b200_state* st, void* peer_amps, int lbit, int my_bit, uint64_t start, uint64_t count) {
   B200_REQUIRE(st != nullptr && peer_amps != nullptr, "b200_peer_swap: null argument");
-  B200_REQUIRE(start <= st->dim && count <= st->dim - start && peer_start <= st->dim && count <= st->dim - peer_start,
-               "b200_peer_swap: range exceeds the state");
+  B200_REQUIRE(lbit >= 0 && lbit < st->n && (my_bit == 0 || my_bit == 1), "b200_peer_swap: bad bit");
+  B200_REQUIRE(start <= st->dim / 2 && count <= st->dim / 2 - start, "b200_peer_swap: pair range exceeds half the state");
   if (count == 0) return 0;
   B200_CUDA(cudaSetDevice(st->device));
   const unsigned grid = kSMs * 8;
-  k_peer_swap<<<grid, 256, 0, st->stream>>>(st->amp + start, static_cast<c128*>(peer_amps) + peer_start, count);
+  k_peer_swap<<<grid, 256, 0, st->stream>>>(st->amp, static_cast<c128*>(peer_amps), start, count, lbit, my_bit);
   st->launches++;
   B200_CUDA(cudaGetLastError());
   B200_CUDA(cudaStreamSynchronize(st->stream));

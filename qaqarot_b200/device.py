@@ -167,9 +167,9 @@ class DeviceState:
     def ipc_close(self, peer_ptr: int) -> None:
         _lib.check(self._lib.b200_ipc_close(C.c_void_p(peer_ptr)))
 
-    def peer_swap(self, peer_ptr: int, start: int, peer_start: int, count: int) -> None:
-        """amp[start + i] <-> peer[peer_start + i], i < count (synchronous)."""
-        _lib.check(self._lib.b200_peer_swap(self._h, C.c_void_p(peer_ptr), start, peer_start, count))
+    def peer_swap(self, peer_ptr: int, lbit: int, my_bit: int, start: int, count: int) -> None:
+        """Pairs [start, start + count): amp[i | lbit = 1 - my_bit] <-> peer[i | lbit = my_bit] (synchronous)."""
+        _lib.check(self._lib.b200_peer_swap(self._h, C.c_void_p(peer_ptr), lbit, my_bit, start, count))
 
     def cond_probs(self, fixed_mask: int, qubit: int, group_bits: np.ndarray) -> np.ndarray:
         """(n_groups, 2): sum |amp|^2 of every group with bit `qubit` = 0 / 1 (qubit < 0: whole group, 0)."""

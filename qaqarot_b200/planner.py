@@ -150,6 +150,76 @@ def fold_conjugated_phases(prims: Sequence[Prim]) -> List[Prim]:
     return out
 
 
+def _prim_sets(p: Prim) -> Tuple[FrozenSet[int], FrozenSet[int]]:
+    """(wires on which the primitive is non-diagonal, wires on which it is diagonal)."""
+    if p.kind == "swap":
+        return frozenset((p.target, p.aux)), frozenset()
+    if p.kind == "x" or (p.kind == "mat" and not _is_diag(_as_matrix(p))):
+        return frozenset((p.target,)), frozenset(p.controls)
+    return frozenset(), frozenset((p.target,) + tuple(p.controls))
+
+
+def shard_schedule(prims: Sequence[Prim], n: int, n_local: int, pos0: Sequence[int]) -> List[Prim]:
+    """Reorder the primitives of a sharded program into *epochs* and insert the exchanges between them.
+
+    Within an epoch the set of global wires is fixed; every primitive whose non-diagonal target is local and
+    that commutes with all primitives deferred before it runs now (two primitives commute unless they share a
+    wire on which one of them is non-diagonal), the others wait.  When nothing more can run, the global wires
+    the waiting primitives need first come home, in exchange for the local wires whose next non-diagonal use is
+    farthest away (Belady; wires on the low index bits stay local).  A brick-pattern circuit thus runs a whole
+    light-cone triangle per epoch instead of paying one exchange per global wire per layer."""
+    g = n - n_local
+    if g <= 0:
+        return list(prims)
+    pos = list(pos0)
+    glob = {w for w in range(n) if pos[w] >= n_local}
+    sets = [_prim_sets(p) for p in prims]
+    out: List[Prim] = []
+    pending = list(range(len(prims)))
+    while pending:
+        skipped_nd: set = set()
+        skipped_dg: set = set()
+        deferred: List[int] = []
+        frontier: List[int] = []                      # global wires that alone keep a primitive from running
+        for i in pending:
+            p = prims[i]
+            nd, dg = sets[i]
+            ok = not (any(q in skipped_nd or q in skipped_dg for q in nd) or any(q in skipped_nd for q in dg))
+            if ok and p.kind != "swap" and nd & glob:
+                ok = False
+                frontier += [q for q in nd & glob if q not in frontier]
+            if ok:
+                out.append(p)
+                if p.kind == "swap":                      # relabelling: the two names trade places
+                    a, b = p.target, p.aux
+                    pos[a], pos[b] = pos[b], pos[a]
+                    if (a in glob) != (b in glob):
+                        glob ^= {a, b}
+            else:
+                deferred.append(i)
+                skipped_nd |= nd
+                skipped_dg |= dg
+        pending = deferred
+        if not pending:
+            break
+        want: List[int] = frontier[:g]
+        next_use = {}
+        for rank_, i in enumerate(pending):
+            for q in sets[i][0]:
+                next_use.setdefault(q, rank_)
+        if not want:
+            raise RuntimeError("sharded planner is stuck without a global wire to bring home")
+        far = len(pending) + 1
+        cand = [w for w in range(n) if w not in glob]
+        cand.sort(key=lambda w: (pos[w] < 4, -next_use.get(w, far), -pos[w]))
+        for w_in, w_out in zip(want, cand):
+            out.append(Prim("exchange", w_in, aux=w_out))
+            pos[w_in], pos[w_out] = pos[w_out], pos[w_in]
+            glob.discard(w_in)
+            glob.add(w_out)
+    return out
+
+
 class Normalized:
     def __init__(self):
         self.items: List[Item] = []
@@ -266,9 +336,10 @@ def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = 
         else:
             push(Item("mat", t=q, m=m, n_prims=cnt), last_touch[q])
 
-    n_in = len(prims)
     prims = fold_conjugated_phases(prims)
     pos = list(initial_pos) if initial_pos is not None else list(range(n))   # wire -> index bit of its data
+    if n_local < n:
+        prims = shard_schedule(prims, n, n_local, pos)
     wire_at = [0] * n
     for w_, p_ in enumerate(pos):
         wire_at[p_] = w_
@@ -276,7 +347,7 @@ def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = 
     if n_local < n:
         for i, p in enumerate(prims):
             if p.kind in ("mat", "x") and not (p.kind == "mat" and _is_diag(_as_matrix(p))):
-                uses[p.target].append(i)
+                uses[p.target].append(i)          # (bring_home below is only a safety net after shard_schedule)
     use_ptr = [0] * n
 
     def move(a: int, b: int):
@@ -311,6 +382,14 @@ def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = 
         return top
 
     for i_prim, p in enumerate(prims):
+        if p.kind == "exchange":                  # from shard_schedule: wire p.target comes home, p.aux leaves
+            gpos, lbit = pos[p.target], pos[p.aux]
+            if pending[lbit] is not None and not _is_diag(pending[lbit]):
+                flush(lbit)                       # a non-diagonal 2x2 must be applied while its wire is local
+            push(Item("exchange", t=lbit, aux=gpos, n_prims=0))
+            move(lbit, gpos)
+            out.n_exchanges += 1
+            continue
         out.n_prims += 1
         if p.kind == "swap":
             a, b = p.target, p.aux

@@ -253,39 +253,48 @@ class ShardedState:
         if program.final_pos:
             self.layout = list(program.final_pos)
 
-    def exchange(self, top: int, gpos: int) -> None:
-        """Swap index bit `top` (must be the top local bit) with global bit `gpos`: trade the half of the shard
-        whose top bit differs from this rank's bit `gpos` with the partner rank.  Layout is the caller's job.
+    def exchange(self, lbit: int, gpos: int) -> None:
+        """Swap local index bit `lbit` with global bit `gpos`: this rank trades the half of its shard whose bit
+        `lbit` differs from its own bit `gpos` with the partner rank.  The wire layout is the caller's job.
 
         On GPUs the two partners swap in place over NVLink with one kernel each (csrc/permute.cu k_peer_swap on
-        the partner's shard mapped through CUDA IPC), each taking one half of the range; ``use_p2p = False`` or a
-        host stand-in falls back to NCCL / gloo send-recv through a bounce buffer."""
+        the partner's shard mapped through CUDA IPC), each taking one half of the pairs; ``use_p2p = False`` or a
+        host stand-in falls back to NCCL / gloo send-recv of the contiguous top half through a bounce buffer
+        (with a local transposition before and after when `lbit` is not the top bit)."""
         torch, dist = _torch()
         import time
-        assert top == self.n_local - 1 and gpos >= self.n_local
+        assert 0 <= lbit < self.n_local <= gpos < self.n_qubits
         partner = self.rank ^ (1 << (gpos - self.n_local))
-        half = 1 << (self.n_local - 1)                          # amplitudes
+        half = 1 << (self.n_local - 1)                          # amplitudes that leave (and arrive)
         self.local.before_comm()
         dist.barrier(group=self.group)                          # both shards are quiescent
         t0 = time.perf_counter()
         if self.use_p2p and isinstance(self.local, _CudaLocal):
             peer = self._peer_pointer(partner)
-            # element (top = 1, global bit 0, rest x) <-> (top = 0, global bit 1, rest x): on the rank whose bit is 0
-            # that is mine[half + x] <-> peer[x], on its partner mine[x] <-> peer[half + x]
-            mine0 = half if self._my_bit(gpos) == 0 else 0
-            peer0 = half - mine0
             if half == 1:
                 lo, cnt = 0, (1 if self.rank < partner else 0)
             else:
-                lo, cnt = (0 if self.rank < partner else half // 2), half // 2     # each partner moves half the range
-            self.st.peer_swap(peer, mine0 + lo, peer0 + lo, cnt)
+                lo, cnt = (0 if self.rank < partner else half // 2), half // 2     # each partner moves half the pairs
+            self.st.peer_swap(peer, lbit, self._my_bit(gpos), lo, cnt)
         else:
+            top = self.n_local - 1
+            if lbit != top:
+                self._local_transpose(lbit, top)
             self._exchange_sendrecv(partner, half, gpos)
+            if lbit != top:
+                self._local_transpose(lbit, top)
         self.local.after_comm()
         dist.barrier(group=self.group)
         self.exchange_ms += (time.perf_counter() - t0) * 1e3
         self.exchange_bytes += 16 * half
         self.n_exchanges += 1
+
+    def _local_transpose(self, a: int, b: int) -> None:
+        prog = Program()
+        woff = prog.add_words([min(a, b) | (max(a, b) << 8)])
+        prog.add_op(_lib.OP_PERMUTE, woff=woff, wlen=1)
+        self.st.apply(prog)
+        self.local.before_comm()
 
     def _peer_pointer(self, partner: int) -> int:
         torch, dist = _torch()
@@ -316,30 +325,16 @@ class ShardedState:
             region.copy_(tmp)
 
     def _make_local(self, wires: Sequence[int]) -> None:
-        """Bring every wire in `wires` onto a local index bit (used by measurement / X-Y expectation values)."""
+        """Bring every wire in `wires` onto a local index bit (used by X / Y expectation values)."""
         need = [w for w in wires if self.layout[w] >= self.n_local]
-        if not need:
-            return
         keep = set(self.layout[w] for w in wires)
-        top = self.n_local - 1
         for w in need:
             inv = self._wire_at()
-            if top in keep:                                      # park an uninvolved local wire on the top bit first
-                victim = max(p for p in range(self.n_local) if p not in keep)
-                prog = Program()
-                woff = prog.add_words([victim | (top << 8)])
-                prog.add_op(_lib.OP_PERMUTE, woff=woff, wlen=1)
-                self.st.apply(prog)
-                a, b = inv[victim], inv[top]
-                self.layout[a], self.layout[b] = top, victim
-                keep.discard(top)
-                keep.add(victim)
-                inv = self._wire_at()
+            victim = max(p for p in range(self.n_local) if p not in keep)
             gpos = self.layout[w]
-            self.exchange(top, gpos)
-            evicted = inv[top]
-            self.layout[w], self.layout[evicted] = top, gpos
-            keep.add(top)
+            self.exchange(victim, gpos)
+            self.layout[w], self.layout[inv[victim]] = victim, gpos
+            keep.add(victim)
 
     # -- measurement ------------------------------------------------------------------------------
     def norm2(self) -> float:
