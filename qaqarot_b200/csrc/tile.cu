@@ -20,7 +20,9 @@
 // thread bits a per-thread predicate, bits outside the tile a per-tile (CTA-uniform) predicate.
 //
 // Descriptor (uint64 words, produced by qaqarot_b200/planner.py::encode_pass; `reals` = float64 pool):
-//   D[0] = A | c<<8 | R<<16 | n_rounds<<24 | n_fans<<32          D[1], D[2] = tile bit positions, 8 bits each
+//   D[0] = A | c<<8 | R<<16 | n_rounds<<24 | n_fans<<32 | flags<<40   D[1], D[2] = tile bit positions, 8 bits each
+//          flags: 1 = the first round loads straight from HBM, 2 = the last round stores straight to HBM (its
+//          register bits avoid the c row bits, so a half warp still covers one contiguous 2^c * 16 B row)
 //   D[3] = fan directory offset | rounds offset << 32      D[4] = first payload real | payload length << 32
 //          (everything the pass reads from `reals` is that one range; each CTA keeps a copy in shared memory)
 //   fan directory: n_fans word offsets; fan record: n_entries | roff<<32, then n_entries masks.
@@ -38,6 +40,7 @@
 #include "common.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace b200 {
 
@@ -188,31 +191,44 @@ __device__ __forceinline__ void fan_apply(c128 (&v)[1 << R], c128 wt, const doub
   }
 }
 
-// Both stages of one record for register bit J (J = R: diag stage only).
-template <int R, int J, int NWARP_T>
-__device__ __forceinline__ void run_record(c128 (&v)[1 << R], uint32_t tk, bool cond, uint32_t dk, uint32_t rm,
-                                           const double* __restrict__ pay_t, const double* __restrict__ pay_d,
-                                           c128 wt) {
-  if constexpr (J < R) {
-    if (!cond) {
-      if (tk == T_MATR) mat_r<R, J, false>(v, pay_t, 0);
-      if (tk == T_MATC) mat_c<R, J, false>(v, pay_t, 0);
-      if (tk == T_X) perm_x<R, J, false>(v, 0);
-    } else {
-      if (tk == T_MATR) mat_r<R, J, true>(v, pay_t, rm);
-      if (tk == T_MATC) mat_c<R, J, true>(v, pay_t, rm);
-      if (tk == T_X) perm_x<R, J, true>(v, rm);
-    }
+// The two stages of a record are dispatched by two dense switches (one indirect branch each) on keys computed
+// once per CTA: a chain of `if (j == J)` / `if (kind == K)` tests cost ~15 dependent branches per record, which
+// two warps per scheduler cannot hide (clock64 phase timing: ~550 idle cycles per record in the gate phase).
+//   key1 = 8 j + target kind + 4 (register-bit controls present)      (0: no target stage)
+//   key2 = 4 j + diag kind, j = R for "every amplitude"               (0: no diag stage)
+template <int R>
+__device__ __forceinline__ void run_target(c128 (&v)[1 << R], uint32_t key1, uint32_t rm, const double* __restrict__ pay) {
+  switch (key1) {
+#define B200_T_CASES(J)                                                                           \
+    case 8 * J + T_MATC: mat_c<R, (J < R ? J : 0), false>(v, pay, 0); break;                        \
+    case 8 * J + T_MATR: mat_r<R, (J < R ? J : 0), false>(v, pay, 0); break;                        \
+    case 8 * J + T_X: perm_x<R, (J < R ? J : 0), false>(v, 0); break;                               \
+    case 8 * J + T_MATC + 4: mat_c<R, (J < R ? J : 0), true>(v, pay, rm); break;                    \
+    case 8 * J + T_MATR + 4: mat_r<R, (J < R ? J : 0), true>(v, pay, rm); break;                    \
+    case 8 * J + T_X + 4: perm_x<R, (J < R ? J : 0), true>(v, rm); break;
+    B200_T_CASES(0) B200_T_CASES(1) B200_T_CASES(2) B200_T_CASES(3)
+#undef B200_T_CASES
+    default: break;
   }
-  if (dk == D_FANT) fant_apply<R, J>(v, wt);
-  if (dk == D_FAN) fan_apply<R, J>(v, wt, reinterpret_cast<const double2*>(pay_d) + 32 + NWARP_T);
-  if constexpr (J >= R) {
-    if (dk == D_PHASE) {
-      const double wx = pay_d[0], wy = pay_d[1];
+}
+template <int R, int NWARP_T>
+__device__ __forceinline__ void run_diag(c128 (&v)[1 << R], uint32_t key2, uint32_t rm, const double* __restrict__ pay,
+                                         c128 wt) {
+  const double2* __restrict__ reg_t = reinterpret_cast<const double2*>(pay) + 32 + NWARP_T;
+  switch (key2) {
+#define B200_D_CASES(J)                                                                           \
+    case 4 * J + D_FANT: fant_apply<R, (J < R ? J : R)>(v, wt); break;                              \
+    case 4 * J + D_FAN: fan_apply<R, (J < R ? J : R)>(v, wt, reg_t); break;
+    B200_D_CASES(0) B200_D_CASES(1) B200_D_CASES(2) B200_D_CASES(3) B200_D_CASES(4)
+#undef B200_D_CASES
+    case 4 * 4 + D_PHASE: {
+      const double wx = pay[0], wy = pay[1];
 #pragma unroll
       for (int rho = 0; rho < (1 << R); ++rho)
         if ((rho & rm) == rm) amp_mul(v[rho], wx, wy, -wy);
+      break;
     }
+    default: break;
   }
 }
 
@@ -224,9 +240,9 @@ constexpr int kMaxGates = 160;     // per pass
 constexpr int kMaxRounds = 8;
 constexpr int kSpreadTabs = 5;     // 6 bits of the tile number each: up to 30 non-tile index bits
 
-constexpr int kMaxPayload = 3072;  // float64 payload of one pass kept in shared memory (planner.MAX_PAYLOAD)
-constexpr int kMaxFanWords = 1024; // directory + records of the pass's fans (planner keeps a pass below this)
-// record (one uint4): x = target kind | j<<4 | diag kind<<8 | (reg_mask != 0)<<12 | fan<<16 | fixed mask bits 32..39<<24
+constexpr int kMaxPayload = 2048;  // float64 payload of one pass kept in shared memory (planner.MAX_PAYLOAD)
+constexpr int kMaxFanWords = 512;  // directory + records of the pass's fans (planner keeps a pass below this)
+// record (one uint4): x = key1 | key2<<8 | fan<<16 | fixed mask bits 32..39<<24
 //                     y = thread mask | reg mask<<16    z = target payload | diag payload<<16 (complex units, relative)
 //                     w = fixed mask bits 0..31
 
@@ -236,7 +252,7 @@ struct RoundHdr {                  // 16 bytes
   uint32_t pad;
 };
 
-template <int A>
+template <int A, int R>
 struct TileSmem {
   c128 tile[1 << A];
   c128 fix[kMaxFans];
@@ -245,20 +261,23 @@ struct TileSmem {
   double pay[kMaxPayload];         // the pass's matrices, phases and fan tables
   uint64_t fanw[kMaxFanWords];     // fan directory and records (entry counts, payload offsets, fixed-bit masks)
   RoundHdr rh[kMaxRounds];
-  uint32_t thr[kMaxRounds][1 << (A - 4)];   // per round, per thread: local index bits | swizzled byte offset / 16 << 16
+  uint32_t thr[kMaxRounds][1 << (A - R)];   // per round, per thread: local index bits | swizzled byte offset / 16 << 16
   uint32_t round_off[kMaxRounds];
+  // direct global <-> register access of the first / last round (when its register bits avoid the row bits):
+  uint64_t gthr[2][1 << (A - R)];  // per thread: where its thread bits sit in the index space
+  uint64_t ghb[2][4];              // per register bit: its index bit as a mask
 };
 
 // ---- the kernel ------------------------------------------------------------------------------------------------
 template <int A, int R, int MINB>
 __global__ void __launch_bounds__(1 << (A - R), MINB)
 k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const uint64_t* __restrict__ desc,
-       const double* __restrict__ reals) {
-  static_assert(R == 4, "the record dispatch assumes 4 register bits");
+       const double* __restrict__ reals, unsigned long long* __restrict__ phase_cycles, uint32_t flags) {
+  static_assert(R == 3 || R == 4, "the record dispatch handles 3 or 4 register bits");
   constexpr int NT = 1 << (A - R), PER = 1 << R, NTB = A - R;
   constexpr int NWARP_T = (NTB > 5) ? (1 << (NTB - 5)) : 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  TileSmem<A>& S = *reinterpret_cast<TileSmem<A>*>(smem_raw);
+  TileSmem<A, R>& S = *reinterpret_cast<TileSmem<A, R>*>(smem_raw);
   c128* const sm = S.tile;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -267,6 +286,7 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
   const uint32_t dir_off = (uint32_t)(desc[3] & 0xFFFFFFFFu), rounds_off = (uint32_t)(desc[3] >> 32);
   const int c_bits = (int)((h0 >> 8) & 0xFF);
   const uint32_t pay_lo = (uint32_t)(desc[4] & 0xFFFFFFFFu), pay_len = (uint32_t)(desc[4] >> 32);
+  const bool direct_in = ((h0 >> 40) & 1) != 0, direct_out = ((h0 >> 41) & 1) != 0;
 
   // ---- one-time setup ----------------------------------------------------------------------------------------
   if (tid == 0) {
@@ -294,6 +314,17 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
     uint32_t lt = 0;
     for (int b = 0; b < NTB; ++b) lt |= ((tid >> b) & 1u) << byte_of(o_lo, o_hi, R + b);
     S.thr[rd][tid] = lt | (swz(lt) << 16);
+    if (rd == 0 || rd == n_rounds - 1) {
+      uint64_t go = 0;
+      for (int b = 0; b < A; ++b) go |= (uint64_t)((lt >> b) & 1u) << byte_of(tb_lo, tb_hi, b);
+      if (rd == 0) S.gthr[0][tid] = go;
+      if (rd == n_rounds - 1) S.gthr[1][tid] = go;
+      if (tid < R) {
+        const uint64_t hbm = 1ull << byte_of(tb_lo, tb_hi, byte_of(o_lo, o_hi, tid));
+        if (rd == 0) S.ghb[0][tid] = hbm;
+        if (rd == n_rounds - 1) S.ghb[1][tid] = hbm;
+      }
+    }
     if (tid < R) S.rh[rd].srb[tid] = (uint16_t)swz(1u << byte_of(o_lo, o_hi, tid));
     const int ng = S.rh[rd].n_gates, first = S.rh[rd].first;
     for (int gi = tid; gi < ng; gi += NT) {
@@ -303,8 +334,10 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
       const uint32_t lm = (uint32_t)((g0 >> 32) & 0xFFFF), rm = (uint32_t)((g0 >> 48) & 0xFFFF);
       const uint32_t pt = tk == T_NONE || tk == T_X ? 0u : (((uint32_t)roffs - pay_lo) >> 1);
       const uint32_t pd = dk == D_NONE ? 0u : (((uint32_t)(roffs >> 32) - pay_lo) >> 1);
-      S.rec[first + gi] = make_uint4(tk | ((j > R ? R : j) << 4) | (dk << 8) | ((rm != 0 && tk != T_NONE) ? 1u << 12 : 0u) |
-                                         (fan << 16) | ((uint32_t)(fm >> 32) << 24),
+      const uint32_t jj = j < (uint32_t)R ? j : 4u;            // 4 = no register target ("every amplitude")
+      const uint32_t key1 = tk == T_NONE ? 0u : 8u * jj + tk + (rm != 0 ? 4u : 0u);
+      const uint32_t key2 = dk == D_NONE ? 0u : 4u * jj + dk;
+      S.rec[first + gi] = make_uint4(key1 | (key2 << 8) | (fan << 16) | ((uint32_t)(fm >> 32) << 24),
                                      lm | (rm << 16), pt | (pd << 16), (uint32_t)fm);
     }
   }
@@ -326,12 +359,21 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
     return b;
   };
 
+  // B200_TILE_TIMING=1: warp 0 / lane 0 of every CTA accumulates the cycles it spends in each phase of a tile
+  long long tk0 = phase_cycles ? clock64() : 0;
+  auto tick = [&](int phase) {
+    if (phase_cycles && tid == 0) {
+      const long long now = clock64();
+      atomicAdd(phase_cycles + phase, (unsigned long long)(now - tk0));
+      tk0 = now;
+    }
+  };
   for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint64_t base = spread_tile(tile);
     const uint64_t fixedidx = base | index_offset;
     const uint32_t fx_lo = (uint32_t)fixedidx, fx_hi = (uint32_t)(fixedidx >> 32);
     c128* __restrict__ g = amp + base + off_t;
-    if (tile + gridDim.x < n_tiles) {
+    if ((flags & 1u) && tile + gridDim.x < n_tiles) {
       const c128* nb = amp + spread_tile(tile + gridDim.x);
       if (n_rows == (uint32_t)NT) {
         prefetch_l2_bulk(nb + pref_off, row_bytes);
@@ -344,7 +386,23 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
       }
     }
 
-    {
+    c128 v[PER];
+    if (direct_in) {
+      // round 0 keeps no row bit in registers: its 16 amplitudes per thread come straight from HBM, a half
+      // warp per 256-byte row, no shared-memory staging and no barrier before the first gate
+      const c128* __restrict__ gi = amp + base + S.gthr[0][tid];
+      uint64_t hb[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) hb[k] = S.ghb[0][k];
+#pragma unroll
+      for (int rho = 0; rho < PER; ++rho) {
+        uint64_t off = 0;
+#pragma unroll
+        for (int k = 0; k < R; ++k)
+          if ((rho >> k) & 1) off |= hb[k];
+        v[rho] = __ldcg(gi + off);
+      }
+    } else {
       uint64_t hb[R];
 #pragma unroll
       for (int k = 0; k < R; ++k) hb[k] = 1ull << byte_of(tb_lo, tb_hi, NTB + k);
@@ -378,20 +436,21 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
       }
       if (lane == 0) S.fix[f] = cmul(p, w[0]);
     }
-    cp_async_wait_all();
-    __syncthreads();
+    tick(0);                      // issue: loads, fan setup
+    if (!direct_in) cp_async_wait_all();
+    __syncthreads();              // tile (or fan products) ready; also: every warp has left the previous tile
+    tick(1);                      // wait for the tile + barrier
 
     for (int rd = 0; rd < n_rounds; ++rd) {
       const uint4 hq = *reinterpret_cast<const uint4*>(&S.rh[rd]);
       const int ng = (int)(hq.x & 0xFFFFu), first = (int)(hq.x >> 16);
-      const uint32_t srb[4] = {(hq.y & 0xFFFFu) << 4, (hq.y >> 16) << 4, (hq.z & 0xFFFFu) << 4, (hq.z >> 16) << 4};
+      const uint32_t srb[5] = {(hq.y & 0xFFFFu) << 4, (hq.y >> 16) << 4, (hq.z & 0xFFFFu) << 4, (hq.z >> 16) << 4, 0u};
       const uint32_t my = S.thr[rd][tid];
       const uint32_t lt = my & 0xFFFFu, stb = (my >> 16) << 4;
       unsigned char* const smb = reinterpret_cast<unsigned char*>(sm);
 
       // Gray-code walk over the 2^R register amplitudes: one XOR per shared-memory address
-      c128 v[PER];
-      {
+      if (!(direct_in && rd == 0)) {
         uint32_t s = stb;
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
@@ -399,7 +458,7 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
           v[i ^ (i >> 1)] = *reinterpret_cast<const c128*>(smb + s);
         }
       }
-
+      tick(2);                    // round: registers <- shared memory
       // the next record is fetched while the current one runs
       uint4 q = S.rec[first];
       for (int gi = first; gi < first + ng; ++gi) {
@@ -408,36 +467,48 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
         // fixed-bit condition: CTA-uniform; thread-bit condition: per thread
         const bool active = ((fx_lo & q.w) == q.w) && ((fx_hi & fmh) == fmh) && ((lt & lm) == lm);
         if (active) {
-          const uint32_t tk = q.x & 15u, j = (q.x >> 4) & 15u, dk = (q.x >> 8) & 15u;
-          const bool cond = ((q.x >> 12) & 1u) != 0;
-          const double* __restrict__ pay_t = S.pay + 2 * (q.z & 0xFFFFu);
+          const uint32_t key1 = q.x & 0xFFu, key2 = (q.x >> 8) & 0xFFu;
           const double* __restrict__ pay_d = S.pay + 2 * (q.z >> 16);
           c128 wt = make_double2(1.0, 0.0);
-          if (dk == D_FANT || dk == D_FAN) {
+          if ((key2 & 3u) == D_FANT || (key2 & 3u) == D_FAN) {
             const double2* __restrict__ tab = reinterpret_cast<const double2*>(pay_d);
             wt = cmul(S.fix[(q.x >> 16) & 0xFFu], cmul(tab[lane], tab[32 + (NWARP_T > 1 ? warp : 0)]));
           }
-          if (j == 0) run_record<R, 0, NWARP_T>(v, tk, cond, dk, rm, pay_t, pay_d, wt);
-          if (j == 1) run_record<R, 1, NWARP_T>(v, tk, cond, dk, rm, pay_t, pay_d, wt);
-          if (j == 2) run_record<R, 2, NWARP_T>(v, tk, cond, dk, rm, pay_t, pay_d, wt);
-          if (j == 3) run_record<R, 3, NWARP_T>(v, tk, cond, dk, rm, pay_t, pay_d, wt);
-          if (j >= R) run_record<R, R, NWARP_T>(v, tk, cond, dk, rm, pay_t, pay_d, wt);
+          run_target<R>(v, key1, rm, S.pay + 2 * (q.z & 0xFFFFu));
+          run_diag<R, NWARP_T>(v, key2, rm, pay_d, wt);
         }
         q = nq;
       }
 
-      {
+      tick(3);                    // round: gates
+      if (direct_out && rd == n_rounds - 1) {
+        c128* __restrict__ go = amp + base + S.gthr[1][tid];
+        uint64_t hb[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) hb[k] = S.ghb[1][k];
+#pragma unroll
+        for (int rho = 0; rho < PER; ++rho) {
+          uint64_t off = 0;
+#pragma unroll
+          for (int k = 0; k < R; ++k)
+            if ((rho >> k) & 1) off |= hb[k];
+          __stcg(go + off, v[rho]);
+        }
+        tick(4);
+      } else {
         uint32_t s = stb;
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
           if (i) s ^= srb[ctz_c(i)];
           *reinterpret_cast<c128*>(smb + s) = v[i ^ (i >> 1)];
         }
+        tick(4);                  // round: shared memory <- registers
+        __syncthreads();
       }
-      __syncthreads();
+      tick(5);                    // round: barrier
     }
 
-    {
+    if (!direct_out) {
       uint64_t hb[R];
 #pragma unroll
       for (int k = 0; k < R; ++k) hb[k] = 1ull << byte_of(tb_lo, tb_hi, NTB + k);
@@ -450,14 +521,18 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
         g[off] = *reinterpret_cast<const c128*>(reinterpret_cast<unsigned char*>(sm) + (sw_t ^ (swz_c((uint32_t)i * NT) << 4)));
       }
     }
-    __syncthreads();     // the next tile's cp.async must not overwrite slots still being read
+    tick(6);                      // stream the tile back
+    // the next tile's cp.async must not overwrite slots still being read (a direct first round writes shared
+    // memory only after the barrier at the head of the next tile)
+    if (!(direct_in && direct_out)) __syncthreads();
+    tick(7);                      // end-of-tile barrier
   }
 }
 
 template <int A, int R, int MINB>
 static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals) {
   constexpr int NT = 1 << (A - R);
-  const size_t smem = sizeof(TileSmem<A>);
+  const size_t smem = sizeof(TileSmem<A, R>);
   static bool configured[64] = {};
   if (!configured[st->device & 63]) {
     B200_CUDA(cudaFuncSetAttribute(k_tile<A, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -466,11 +541,33 @@ static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals)
   const uint64_t n_tiles = st->dim >> A;
   // persistent: exactly the resident CTAs, each walking tiles blockIdx, blockIdx + grid, ... so that it can
   // prefetch its next tile into L2 while it works on the current one
-  const uint64_t cap = (uint64_t)kSMs * MINB;
+  static const int ctas_env = getenv("B200_TILE_CTAS_PER_SM") ? atoi(getenv("B200_TILE_CTAS_PER_SM")) : 0;   // experiment
+  const uint64_t cap = (uint64_t)kSMs * (ctas_env > 0 && ctas_env < MINB ? ctas_env : MINB);
   const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
-  k_tile<A, R, MINB><<<grid, NT, smem, st->stream>>>(st->amp, n_tiles, st->index_offset, d_desc, d_reals);
+  static const bool timing = getenv("B200_TILE_TIMING") != nullptr;
+  unsigned long long* d_cyc = nullptr;
+  if (timing) {
+    B200_CUDA(cudaMalloc(&d_cyc, 8 * sizeof(unsigned long long)));
+    B200_CUDA(cudaMemsetAsync(d_cyc, 0, 8 * sizeof(unsigned long long), st->stream));
+  }
+  // L2 prefetch of the next tile: measured no gain (the loads of a tile already overlap the other CTA's gates)
+  // and ~2000 cycles per tile spent issuing 256 bulk prefetches; off unless B200_TILE_PREFETCH is set
+  static const uint32_t flags = getenv("B200_TILE_PREFETCH") ? 1u : 0u;
+  k_tile<A, R, MINB><<<grid, NT, smem, st->stream>>>(st->amp, n_tiles, st->index_offset, d_desc, d_reals, d_cyc, flags);
   st->launches++;
   B200_CUDA(cudaGetLastError());
+  if (timing) {
+    unsigned long long h[8];
+    B200_CUDA(cudaMemcpyAsync(h, d_cyc, sizeof h, cudaMemcpyDeviceToHost, st->stream));
+    B200_CUDA(cudaStreamSynchronize(st->stream));
+    B200_CUDA(cudaFree(d_cyc));
+    double tot = 0;
+    for (int i = 0; i < 8; ++i) tot += (double)h[i];
+    fprintf(stderr, "[k_tile A=%d R=%d tiles=%llu ctas=%u] cycles per tile per CTA:", A, R, (unsigned long long)n_tiles, grid);
+    static const char* names[8] = {"issue", "wait", "rd_load", "rd_gates", "rd_store", "rd_barrier", "tile_store", "end_barrier"};
+    for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%.0f", names[i], (double)h[i] / (double)n_tiles);
+    fprintf(stderr, " total=%.0f\n", tot / (double)n_tiles);
+  }
   return 0;
 }
 
@@ -481,7 +578,7 @@ int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_d
   const int A = (int)(h0 & 0xFF), c = (int)((h0 >> 8) & 0xFF), R = (int)((h0 >> 16) & 0xFF);
   const int n_rounds = (int)((h0 >> 24) & 0xFF), n_fans = (int)((h0 >> 32) & 0xFF);
   char msg[200];
-  if (A > st->n || c > A || R != 4 || n_fans > kMaxFans || n_rounds > kMaxRounds ||
+  if (A > st->n || c > A || (R != 4 && !(R == 3 && A == 11)) || n_fans > kMaxFans || n_rounds > kMaxRounds ||
       st->n - A > 6 * kSpreadTabs) {
     snprintf(msg, sizeof msg, "TILE descriptor not executable: A=%d c=%d R=%d fans=%d rounds=%d on %d qubits", A, c, R,
              n_fans, n_rounds, st->n);
@@ -514,7 +611,7 @@ int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_d
   switch (A) {
     case 9:  return launch<9, 4, 8>(st, d_desc, d_reals);
     case 10: return launch<10, 4, 8>(st, d_desc, d_reals);
-    case 11: return launch<11, 4, 4>(st, d_desc, d_reals);
+    case 11: return R == 3 ? launch<11, 3, 3>(st, d_desc, d_reals) : launch<11, 4, 4>(st, d_desc, d_reals);
     case 12: return launch<12, 4, 2>(st, d_desc, d_reals);
     case 13: return launch<13, 4, 1>(st, d_desc, d_reals);
     default:

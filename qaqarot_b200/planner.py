@@ -34,8 +34,8 @@ from .program import Program
 T_NONE, T_MATC, T_MATR, T_X = 0, 1, 2, 3          # target stage of a tile gate record
 D_NONE, D_FANT, D_FAN, D_PHASE = 0, 1, 2, 3         # diagonal stage (fan without / with register table, phase)
 MAX_GATES = 160          # per pass (record slots in csrc/tile.cu)
-MAX_PAYLOAD = 3072       # float64 payload of one pass (shared-memory copy in csrc/tile.cu)
-MAX_FAN_WORDS = 1024     # fan directory + records of one pass (shared-memory copy in csrc/tile.cu)
+MAX_PAYLOAD = 2048       # float64 payload of one pass (shared-memory copy in csrc/tile.cu)
+MAX_FAN_WORDS = 512      # fan directory + records of one pass (shared-memory copy in csrc/tile.cu)
 MAX_FANS = 64            # per pass (shared-memory slots in csrc/tile.cu)
 
 
@@ -48,6 +48,8 @@ class PlanConfig:
     min_qubits: int = 9       # below this the state is tiny: one kernel per gate
     max_cost: float = 150.0   # DFMA-equivalents per amplitude per pass before a new pass is opened
     scan_limit: int = 4096    # how far ahead of the first unscheduled item a pass may look
+    direct_io: bool = False   # let a first / last round bypass shared memory (measured neutral at A = 12: the
+                              # loads and stores of a tile then stall the issuing warps instead of cp.async)
     kernel_tiles: Tuple[int, ...] = (9, 10, 11, 12, 13)   # tile sizes csrc/tile.cu instantiates (r = 4)
 
 
@@ -644,7 +646,7 @@ def _pack8(vals: Sequence[int]) -> Tuple[int, int]:
     return lo, hi
 
 
-def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int) -> None:
+def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int, direct_io: bool = False) -> None:
     a = len(ps.tile)
     tile = ps.tile
     loc = {q: i for i, q in enumerate(tile)}
@@ -781,7 +783,14 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int) -> None:
         directory.append(base + len(body))
         body += rec
     rounds_off = base + len(body)
-    words = [a | (c << 8) | (r << 16) | (len(ps.rounds) << 24) | (n_fans << 32), t_lo, t_hi,
+    # first / last round may bypass shared memory when none of the row bits (local 0..c-1) is a register bit:
+    # the thread order then maps lanes 0..2^c-1 onto one contiguous row (see _thread_order)
+    def _direct(order):
+        return c >= 3 and all(b >= c for b in order[:r]) and order[r:r + c] == list(range(c))
+    flags = 0
+    if direct_io:
+        flags = (1 if _direct(encoded_rounds[0][0]) else 0) | (2 if _direct(encoded_rounds[-1][0]) else 0)
+    words = [a | (c << 8) | (r << 16) | (len(ps.rounds) << 24) | (n_fans << 32) | (flags << 40), t_lo, t_hi,
              5 | (rounds_off << 32), pay_lo | (pay_len << 32)] + directory + body + round_words
     woff = prog.add_words(words)
     prog.add_op(_lib.OP_TILE, woff=woff, wlen=len(words), nbytes=32.0 * 2 ** n)
@@ -860,7 +869,7 @@ def plan(prims: Sequence[Prim], n_qubits: int, cfg: PlanConfig = DEFAULT, n_loca
         ps, rest = build_pass(remaining, nl, a, r, c, cfg)
         if not ps.rounds:                                   # cannot happen: the head item always fits
             raise RuntimeError(f"planner made no progress at {remaining[0]}")
-        encode_pass(prog, ps, nl, r, c)
+        encode_pass(prog, ps, nl, r, c, cfg.direct_io)
         remaining = rest
     if sharded:
         prog.n_prims += norm.n_relabelled

@@ -195,6 +195,47 @@ def test_tile_kernel_sizes_against_oracle(a, extra):
     assert maxabs(got, _oracle(circ, initial=init)) <= TOL
 
 
+@pytest.mark.parametrize("n", [12, 15, 18])
+def test_tile_kernel_direct_first_and_last_round(n):
+    """First round loaded from / last round stored to HBM directly (PlanConfig.direct_io), bypassing shared memory."""
+    from qaqarot_b200.planner import PlanConfig
+    from qaqarot_b200 import workloads as W
+    rng = np.random.default_rng(400 + n)
+    for circ in (W.qft(n), W.random_layers(n, 6), C.build(Circuit, {"n": n, "ops": C.random_ops(rng, n, 150, True)})):
+        be = B200Backend(plan_config=PlanConfig(a=min(n, 12), direct_io=True))
+        try:
+            got = circ.run(backend=be)
+            words = be._compiled.prefix._words
+            flagged = [((words[o[5]] >> 40) & 3) for o in be._compiled.prefix._ops if o[0] == 16]
+        finally:
+            be.close()
+        assert any(flagged)
+        assert maxabs(got, _oracle(circ)) <= TOL
+
+
+@pytest.mark.parametrize("n", [11, 13, 17])
+def test_tile_kernel_three_register_bits(n):
+    """The 2^11-amplitude tile with 3 register bits per round (8 amplitudes per thread, 3 CTAs per SM)."""
+    from qaqarot_b200.planner import PlanConfig
+    rng = np.random.default_rng(300 + n)
+    init = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
+    init /= np.linalg.norm(init)
+    circ = C.build(Circuit, {"n": n, "ops": C.random_ops(rng, n, 150, True)})
+    be = B200Backend(plan_config=PlanConfig(a=11, r=3))
+    try:
+        got = circ.run(backend=be, initial=init)
+    finally:
+        be.close()
+    assert maxabs(got, _oracle(circ, initial=init)) <= TOL
+    from qaqarot_b200 import workloads as W
+    q = W.qft(n)
+    be = B200Backend(plan_config=PlanConfig(a=11, r=3))
+    try:
+        assert maxabs(q.run(backend=be), _oracle(q)) <= TOL
+    finally:
+        be.close()
+
+
 def test_tile_kernel_matches_descriptor_interpreter():
     """Same encoded program on the CUDA executor and on the numpy interpreter of the descriptor."""
     from oracle.program_interp import OracleState
