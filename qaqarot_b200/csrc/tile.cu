@@ -518,7 +518,7 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
 #pragma unroll
         for (int k = 0; k < R; ++k)
           if ((i >> k) & 1) off |= hb[k];
-        g[off] = *reinterpret_cast<const c128*>(reinterpret_cast<unsigned char*>(sm) + (sw_t ^ (swz_c((uint32_t)i * NT) << 4)));
+        __stcs(g + off, *reinterpret_cast<const c128*>(reinterpret_cast<unsigned char*>(sm) + (sw_t ^ (swz_c((uint32_t)i * NT) << 4))));
       }
     }
     tick(6);                      // stream the tile back
