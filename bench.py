@@ -248,8 +248,7 @@ def run_b200(args):
     st.set_profiling(True)
 
     def step():
-        st.set_basis(0)
-        st.apply(prog)
+        st.apply(prog, init_basis=0)             # prepare |0..0> + the whole program (B200_OP_INIT folded in)
 
     for _ in range(args.warmup):
         step()
@@ -381,8 +380,7 @@ def run_sharded(args, world: int):
     st.set_profiling(True)
 
     def step():
-        st.set_basis(0)
-        st.apply(prog)
+        st.apply(prog, init_basis=0)
 
     def fence():
         st.sync()

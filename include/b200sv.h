@@ -42,7 +42,10 @@ enum {
                          transpositions (p, q).  The planner relabels swap gates and emits at most two of
                          these at the end of a program instead of 3 CX sweeps per swap (gate.py:1172-1177)   */
   B200_OP_TILE  = 16, /* fused tile-resident pass: `woff/wlen` locate its descriptor in `words`            */
-  B200_OP_SCALE = 17  /* multiply the whole state by reals[0..1]                                           */
+  B200_OP_SCALE = 17, /* multiply the whole state by reals[0..1]                                           */
+  B200_OP_INIT  = 18  /* state := |cmask> (prepare(), numpy_backend.py:52-62).  Directly before a TILE op it costs
+                         nothing: that pass synthesises its input instead of reading it (no memset sweep, and the
+                         pass only writes); `cmask` carries the basis index including the shard bits             */
 };
 
 typedef struct b200_op {

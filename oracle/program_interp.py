@@ -63,7 +63,11 @@ class OracleState:
         return c
 
     # -- program execution ----------------------------------------------------------------------
-    def apply(self, program):
+    def apply(self, program, init_basis=None):
+        if init_basis is not None:
+            self.psi[:] = 0.0
+            if (init_basis & ~(self.dim - 1)) == self.index_offset:
+                self.psi[init_basis & (self.dim - 1)] = 1.0
         if len(program) == 0:
             return
         ops, n_ops, words, reals = program.frozen()

@@ -34,6 +34,7 @@ class Op(C.Structure):
 
 
 OP_MAT, OP_DIAG, OP_X, OP_SWAP, OP_PERMUTE, OP_TILE, OP_SCALE = 1, 2, 3, 4, 5, 16, 17
+OP_INIT = 18         # state := |cmask>; free when the next op is a TILE pass
 OP_EXCHANGE = 32      # host-level: exchange index bit `target` (top local) with global bit `aux`; never sent to the C ABI
 
 _lib: Optional[C.CDLL] = None

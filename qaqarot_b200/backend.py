@@ -199,11 +199,12 @@ class B200Backend(_Base):
         ctx.device_state = st
         if cache is not None:
             st.copy_from(cache)
+            st.apply(comp.prefix)
         elif initial is not None:
             st.upload(initial)
+            st.apply(comp.prefix)
         else:
-            st.set_basis(0)
-        st.apply(comp.prefix)
+            st.apply(comp.prefix, init_basis=0)      # |0...0> is synthesised by the first pass (B200_OP_INIT)
         self.last_stats = {"n_gates": comp.n_gates, "prefix_passes": comp.prefix.n_passes,
                            "prefix_prims": comp.prefix.n_prims}
         if not comp.rest:

@@ -492,12 +492,28 @@ int b200_apply_program(b200_state* st, const b200_op* ops, int n_ops, const uint
     st->op_kinds.assign(n_ops, 0);
   }
   B200_CUDA(cudaEventRecord(st->prog.start, st->stream));
+  uint64_t pending_init = kNoInit;
   for (int i = 0; i < n_ops; ++i) {
     const b200_op& op = ops[i];
     if (st->profiling) { B200_CUDA(cudaEventRecord(st->op_events[2 * i], st->stream)); st->op_kinds[i] = op.kind; }
-    if (op.kind == B200_OP_TILE) {
+    if (op.kind == B200_OP_INIT) {
+      const uint64_t lo = op.cmask & (st->dim - 1);
+      B200_REQUIRE(st->n >= 63 || (op.cmask >> st->n) < (1ull << 24), "INIT: basis index out of range");
+      if (i + 1 < n_ops && ops[i + 1].kind == B200_OP_TILE) {
+        pending_init = op.cmask;                           // folded into the next pass
+      } else {
+        B200_CUDA(cudaMemsetAsync(st->amp, 0, sizeof(c128) * st->dim, st->stream));
+        if ((op.cmask & ~(st->dim - 1)) == st->index_offset) {
+          k_set_one<<<1, 1, 0, st->stream>>>(st->amp, lo);
+          st->launches++;
+          B200_CUDA(cudaGetLastError());
+        }
+      }
+    } else if (op.kind == B200_OP_TILE) {
       B200_REQUIRE(op.woff + (uint64_t)op.wlen <= n_words, "TILE descriptor out of range");
-      if (launch_tile_pass(st, st->d_words + op.woff, words + op.woff, op.wlen, st->d_reals, n_reals)) return 1;
+      if (launch_tile_pass(st, st->d_words + op.woff, words + op.woff, op.wlen, st->d_reals, n_reals, pending_init))
+        return 1;
+      pending_init = kNoInit;
     } else if (op.kind == B200_OP_PERMUTE) {
       B200_REQUIRE(op.wlen >= 0 && op.woff + (uint64_t)op.wlen <= n_words, "PERMUTE descriptor out of range");
       if (launch_permute(st, words + op.woff, op.wlen)) return 1;

@@ -272,7 +272,8 @@ struct TileSmem {
 template <int A, int R, int MINB>
 __global__ void __launch_bounds__(1 << (A - R), MINB)
 k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const uint64_t* __restrict__ desc,
-       const double* __restrict__ reals, unsigned long long* __restrict__ phase_cycles, uint32_t flags) {
+       const double* __restrict__ reals, unsigned long long* __restrict__ phase_cycles, uint32_t flags,
+       uint64_t init_tile, uint32_t init_local) {
   static_assert(R == 3 || R == 4, "the record dispatch handles 3 or 4 register bits");
   constexpr int NT = 1 << (A - R), PER = 1 << R, NTB = A - R;
   constexpr int NWARP_T = (NTB > 5) ? (1 << (NTB - 5)) : 1;
@@ -286,7 +287,10 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
   const uint32_t dir_off = (uint32_t)(desc[3] & 0xFFFFFFFFu), rounds_off = (uint32_t)(desc[3] >> 32);
   const int c_bits = (int)((h0 >> 8) & 0xFF);
   const uint32_t pay_lo = (uint32_t)(desc[4] & 0xFFFFFFFFu), pay_len = (uint32_t)(desc[4] >> 32);
-  const bool direct_in = ((h0 >> 40) & 1) != 0, direct_out = ((h0 >> 41) & 1) != 0;
+  // flags bit 1: the state is a basis vector that nobody has written yet -- every tile is all zeros except
+  // tile `init_tile`, whose local index `init_local` holds 1 (B200_OP_INIT folded into this pass)
+  const bool init = (flags & 2u) != 0;
+  const bool direct_in = ((h0 >> 40) & 1) != 0 && !init, direct_out = ((h0 >> 41) & 1) != 0;
 
   // ---- one-time setup ----------------------------------------------------------------------------------------
   if (tid == 0) {
@@ -402,6 +406,11 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
           if ((rho >> k) & 1) off |= hb[k];
         v[rho] = __ldcg(gi + off);
       }
+    } else if (init) {
+#pragma unroll
+      for (int i = 0; i < PER; ++i)
+        *reinterpret_cast<c128*>(reinterpret_cast<unsigned char*>(sm) + (sw_t ^ (swz_c((uint32_t)i * NT) << 4))) =
+            make_double2(0.0, 0.0);
     } else {
       uint64_t hb[R];
 #pragma unroll
@@ -437,8 +446,12 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
       if (lane == 0) S.fix[f] = cmul(p, w[0]);
     }
     tick(0);                      // issue: loads, fan setup
-    if (!direct_in) cp_async_wait_all();
+    if (!direct_in && !init) cp_async_wait_all();
     __syncthreads();              // tile (or fan products) ready; also: every warp has left the previous tile
+    if (init && tile == init_tile) {
+      if (tid == 0) sm[swz(init_local)] = make_double2(1.0, 0.0);
+      __syncthreads();
+    }
     tick(1);                      // wait for the tile + barrier
 
     for (int rd = 0; rd < n_rounds; ++rd) {
@@ -530,7 +543,8 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
 }
 
 template <int A, int R, int MINB>
-static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals) {
+static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals, bool init, uint64_t init_tile,
+                  uint32_t init_local) {
   constexpr int NT = 1 << (A - R);
   const size_t smem = sizeof(TileSmem<A, R>);
   static bool configured[64] = {};
@@ -553,7 +567,8 @@ static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals)
   // L2 prefetch of the next tile: measured no gain (the loads of a tile already overlap the other CTA's gates)
   // and ~2000 cycles per tile spent issuing 256 bulk prefetches; off unless B200_TILE_PREFETCH is set
   static const uint32_t flags = getenv("B200_TILE_PREFETCH") ? 1u : 0u;
-  k_tile<A, R, MINB><<<grid, NT, smem, st->stream>>>(st->amp, n_tiles, st->index_offset, d_desc, d_reals, d_cyc, flags);
+  k_tile<A, R, MINB><<<grid, NT, smem, st->stream>>>(st->amp, n_tiles, st->index_offset, d_desc, d_reals, d_cyc,
+                                                     flags | (init ? 2u : 0u), init_tile, init_local);
   st->launches++;
   B200_CUDA(cudaGetLastError());
   if (timing) {
@@ -572,7 +587,7 @@ static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals)
 }
 
 int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_desc, int wlen,
-                     const double* d_reals, size_t n_reals) {
+                     const double* d_reals, size_t n_reals, uint64_t init_index) {
   B200_REQUIRE(wlen >= 5, "TILE descriptor too short");
   const uint64_t h0 = h_desc[0];
   const int A = (int)(h0 & 0xFF), c = (int)((h0 >> 8) & 0xFF), R = (int)((h0 >> 16) & 0xFF);
@@ -608,12 +623,27 @@ int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_d
     pos += h_desc[pos] >> 16;
   }
   B200_REQUIRE(pos == (uint64_t)wlen && gates <= (uint64_t)kMaxGates, "TILE descriptor: bad round lengths or too many gates");
+  const bool init = init_index != kNoInit;
+  uint64_t init_tile = ~0ull;
+  uint32_t init_local = 0;
+  if (init && (init_index & ~(st->dim - 1)) == st->index_offset) {     // the 1 lives on this shard
+    bool in_tile[64] = {};
+    for (int i = 0; i < A; ++i) {
+      const int b = (int)(((i < 8 ? h_desc[1] : h_desc[2]) >> (8 * (i & 7))) & 0xFF);
+      in_tile[b] = true;
+      init_local |= (uint32_t)((init_index >> b) & 1ull) << i;
+    }
+    init_tile = 0;
+    for (int b = 0, k = 0; b < st->n; ++b)
+      if (!in_tile[b]) init_tile |= ((init_index >> b) & 1ull) << k++;
+  }
   switch (A) {
-    case 9:  return launch<9, 4, 8>(st, d_desc, d_reals);
-    case 10: return launch<10, 4, 8>(st, d_desc, d_reals);
-    case 11: return R == 3 ? launch<11, 3, 3>(st, d_desc, d_reals) : launch<11, 4, 4>(st, d_desc, d_reals);
-    case 12: return launch<12, 4, 2>(st, d_desc, d_reals);
-    case 13: return launch<13, 4, 1>(st, d_desc, d_reals);
+    case 9:  return launch<9, 4, 8>(st, d_desc, d_reals, init, init_tile, init_local);
+    case 10: return launch<10, 4, 8>(st, d_desc, d_reals, init, init_tile, init_local);
+    case 11: return R == 3 ? launch<11, 3, 3>(st, d_desc, d_reals, init, init_tile, init_local)
+                           : launch<11, 4, 4>(st, d_desc, d_reals, init, init_tile, init_local);
+    case 12: return launch<12, 4, 2>(st, d_desc, d_reals, init, init_tile, init_local);
+    case 13: return launch<13, 4, 1>(st, d_desc, d_reals, init, init_tile, init_local);
     default:
       snprintf(msg, sizeof msg, "TILE descriptor: tile size 2^%d is not built (9..13)", A);
       set_error(msg);

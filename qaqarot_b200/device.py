@@ -68,10 +68,13 @@ class DeviceState:
         return c
 
     # -- evolution --------------------------------------------------------------------------------
-    def apply(self, program: Program) -> None:
+    def apply(self, program: Program, init_basis: Optional[int] = None) -> None:
+        """`init_basis`: start from |init_basis> (B200_OP_INIT): replaces a set_basis() sweep before the program."""
         if len(program) == 0:
+            if init_basis is not None:
+                self.set_basis(init_basis & (self.dim - 1))
             return
-        ops, n_ops, words, reals = program.frozen()
+        ops, n_ops, words, reals = program.frozen() if init_basis is None else program.frozen_with_init(init_basis)
         _lib.check(self._lib.b200_apply_program(
             self._h, ops, n_ops, words.ctypes.data_as(C.c_void_p), words.size,
             reals.ctypes.data_as(C.c_void_p), reals.size))

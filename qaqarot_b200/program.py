@@ -70,6 +70,21 @@ class Program:
         self.n_prims += 1
 
     # -- consumption ----------------------------------------------------------------------------
+    def frozen_with_init(self, index: int):
+        """The same program preceded by B200_OP_INIT (state := |index>), for runs that start from a basis state."""
+        key = int(index)
+        cache = self.__dict__.setdefault("_frozen_init", {})
+        if key not in cache or cache[key][0] is not self.frozen():
+            base = self.frozen()
+            ops0, n_ops, words, reals = base
+            ops = (_lib.Op * (n_ops + 1))()
+            ops[0].kind, ops[0].cmask = _lib.OP_INIT, key
+            for i in range(n_ops):
+                for f, _ in _lib.Op._fields_:
+                    setattr(ops[i + 1], f, getattr(ops0[i], f))
+            cache[key] = (base, (ops, n_ops + 1, words, reals))
+        return cache[key][1]
+
     def frozen(self):
         if self._frozen is None:
             ops = (_lib.Op * max(1, len(self._ops)))()

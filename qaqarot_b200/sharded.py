@@ -237,14 +237,20 @@ class ShardedState:
         return c
 
     # -- evolution --------------------------------------------------------------------------------
-    def apply(self, program: Program) -> None:
+    def apply(self, program: Program, init_basis: Optional[int] = None) -> None:
+        if init_basis is not None:
+            self.layout = list(range(self.n_qubits))
+            segs = program.segments()
+            if not segs or not isinstance(segs[0], Program):
+                self.set_basis(init_basis)
+                init_basis = None
         if len(program) == 0 and not program.final_pos:
             return
         if program.initial_pos and list(program.initial_pos) != self.layout:
             raise ValueError("program was planned for a different wire layout than the state is in")
-        for seg in program.segments():
+        for k, seg in enumerate(program.segments()):
             if isinstance(seg, Program):
-                self.st.apply(seg)
+                self.st.apply(seg, init_basis=init_basis if k == 0 else None)
                 if self.profile is not None:
                     ms, kinds = self.st.last_op_times()
                     self.profile.append((kinds.copy(), ms.copy()))
