@@ -363,7 +363,9 @@ def run_sharded(args, world: int):
     from qaqarot_b200 import ShardedB200Backend
     rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    os.environ["NCCL_DEBUG"] = os.environ.get("B200_NCCL_DEBUG", "WARN")     # keep NCCL's banner off stdout
+    # stdout carries exactly one JSON line: send NCCL's version banner / warnings to stderr
+    os.environ["NCCL_DEBUG"] = os.environ.get("B200_NCCL_DEBUG", "WARN")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     wname, n, depth = sharded_workload(args, world)
     circ, wl = build_workload(wname, n, depth)
