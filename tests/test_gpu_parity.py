@@ -283,3 +283,24 @@ def test_permute_kernel_against_interpreter(n):
         got = dev.download()
         dev.close()
         assert np.array_equal(got, ref.psi), pairs
+
+
+def test_c2_qft_30_qubits_against_the_analytic_answer():
+    """BASELINE configs[1] at full size (16 GiB state): windows of the result against
+    exp(2 pi i x y / N) / sqrt(N), the norm, and the known first amplitude."""
+    from qaqarot_b200 import workloads as W
+    n, x = 30, 123456789
+    be = B200Backend()
+    try:
+        ctx = W.qft(n).run(backend=be, returns="_inner_ctx")
+        st = ctx.device_state
+        assert abs(st.norm2() - 1.0) < 1e-10
+        rng = np.random.default_rng(30)
+        starts = [0, (1 << n) - 4096] + [int(s) for s in rng.integers(0, (1 << n) - 4096, 6)]
+        for s in starts:
+            got = st.download(offset=s, count=4096)
+            y = np.arange(s, s + 4096, dtype=np.int64)
+            want = W.qft_analytic_amplitude(n, x, y)
+            assert maxabs(got, want) <= 1e-14        # |amp| = 2^-15, so this is 3e-10 relative
+    finally:
+        be.close()
