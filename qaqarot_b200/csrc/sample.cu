@@ -154,7 +154,57 @@ extern "C" int b200_sample(b200_state* st, const int32_t* order, int m, const do
   std::vector<double> sums;
   uint64_t fixed_mask = 0;
 
-  for (int j = 0; j < m; ++j) {
+  // The first K levels (K <= 10 distinct qubits) cost ONE pass: the marginal distribution of those K qubits is
+  // read off a single conditional-probability reduction with all 2^(K-1) prefixes as groups, and the
+  // conditionals of the levels above it are sums of its entries.  Level by level, each of the first
+  // log2(shots) levels would be a full read of the state.
+  int j0 = 0;
+  {
+    int K = 0;
+    uint64_t seen = 0;
+    while (K < m && K < 10 && !((seen >> order[K]) & 1ull)) seen |= 1ull << order[K++];
+    if (K >= 2) {
+      const int n_groups = 1 << (K - 1);
+      uint64_t mask0 = 0;
+      for (int t = 0; t < K - 1; ++t) mask0 |= 1ull << order[t];
+      group_bits.resize(n_groups);
+      for (int g = 0; g < n_groups; ++g) {
+        uint64_t b = 0;
+        for (int t = 0; t < K - 1; ++t)
+          if ((g >> t) & 1) b |= 1ull << order[t];
+        group_bits[g] = b;
+      }
+      sums.resize(2 * (size_t)n_groups);
+      if (cond_probs(st, mask0, order[K - 1], group_bits.data(), n_groups, sums.data())) return 1;
+      // node[j][p]: probability of the first j outcomes p (bit t of p = outcome of order[t])
+      std::vector<std::vector<double>> node(K + 1);
+      node[K].resize((size_t)1 << K);
+      for (int g = 0; g < n_groups; ++g) {
+        node[K][g] = sums[2 * (size_t)g];
+        node[K][g | (1 << (K - 1))] = sums[2 * (size_t)g + 1];
+      }
+      for (int j = K - 1; j >= 0; --j) {
+        node[j].resize((size_t)1 << j);
+        for (int p = 0; p < (1 << j); ++p) node[j][p] = node[j + 1][p] + node[j + 1][p | (1 << j)];
+      }
+      for (int s = 0; s < n_shots; ++s) {
+        int p = 0;
+        for (int j = 0; j < K; ++j) {
+          const double s0 = node[j + 1][p], s1 = node[j + 1][p | (1 << j)];
+          const double p0 = s0 / (s0 + s1);
+          if (!(uniforms[(size_t)s * m + j] < p0)) {
+            p |= 1 << j;
+            out_bits[s] |= 1ull << j;
+            prefix[s] |= 1ull << order[j];
+          }
+        }
+      }
+      fixed_mask = mask0 | (1ull << order[K - 1]);
+      j0 = K;
+    }
+  }
+
+  for (int j = j0; j < m; ++j) {
     const int q = order[j];
     const uint64_t tbit = 1ull << q;
     if (fixed_mask & tbit) {

@@ -400,7 +400,45 @@ class ShardedState:
         fixed_mask = 0
         lmask = (1 << self.n_local) - 1
         mine = self.rank << self.n_local
+        # first K levels from one reduction (see csrc/sample.cu): marginal table of K distinct qubits
+        j0 = 0
+        K = 0
+        while K < m and K < 10 and order[K] not in order[:K]:
+            K += 1
+        if K >= 2:
+            bits = [self.layout[w] for w in order[:K]]
+            mask0 = sum(1 << b for b in bits[:-1])
+            n_groups = 1 << (K - 1)
+            gb = np.zeros(n_groups, dtype=np.uint64)
+            for t in range(K - 1):
+                gb |= ((np.arange(n_groups, dtype=np.uint64) >> np.uint64(t)) & np.uint64(1)) << np.uint64(bits[t])
+            sums = np.zeros((n_groups, 2))
+            gmask = mask0 & ~lmask
+            here = np.nonzero((gb & np.uint64(~lmask & ((1 << self.n_qubits) - 1))) == np.uint64(mine & gmask))[0]
+            if here.size:
+                local_bits = gb[here] & np.uint64(lmask)
+                pb = bits[-1]
+                if pb < self.n_local:
+                    sums[here] = self.st.cond_probs(mask0 & lmask, pb, local_bits)
+                else:
+                    sums[here, self._my_bit(pb)] = self.st.cond_probs(mask0 & lmask, -1, local_bits)[:, 0]
+            sums = self._allreduce(sums.reshape(-1)).reshape(-1, 2)
+            node = [None] * (K + 1)
+            node[K] = np.concatenate([sums[:, 0], sums[:, 1]])
+            for j in range(K - 1, -1, -1):
+                node[j] = node[j + 1][: 1 << j] + node[j + 1][1 << j:]
+            p = np.zeros(n_shots, dtype=np.int64)
+            for j in range(K):
+                s0, s1 = node[j + 1][p], node[j + 1][p | (1 << j)]
+                bit = ~(uniforms[:, j] < s0 / (s0 + s1))
+                p |= bit.astype(np.int64) << j
+                out |= bit.astype(np.uint64) << np.uint64(j)
+                prefix |= np.where(bit, np.uint64(1 << bits[j]), np.uint64(0))
+            fixed_mask = mask0 | (1 << bits[-1])
+            j0 = K
         for j, wire in enumerate(order):
+            if j < j0:
+                continue
             pb = self.layout[wire]
             tbit = 1 << pb
             if fixed_mask & tbit:
