@@ -269,7 +269,7 @@ struct TileSmem {
 };
 
 // ---- the kernel ------------------------------------------------------------------------------------------------
-template <int A, int R, int MINB>
+template <int A, int R, int MINB, bool TIMING>
 __global__ void __launch_bounds__(1 << (A - R), MINB)
 k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const uint64_t* __restrict__ desc,
        const double* __restrict__ reals, unsigned long long* __restrict__ phase_cycles, uint32_t flags,
@@ -364,9 +364,9 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
   };
 
   // B200_TILE_TIMING=1: warp 0 / lane 0 of every CTA accumulates the cycles it spends in each phase of a tile
-  long long tk0 = phase_cycles ? clock64() : 0;
+  long long tk0 = TIMING ? clock64() : 0;
   auto tick = [&](int phase) {
-    if (phase_cycles && tid == 0) {
+    if (TIMING && tid == 0) {
       const long long now = clock64();
       atomicAdd(phase_cycles + phase, (unsigned long long)(now - tk0));
       tk0 = now;
@@ -549,7 +549,8 @@ static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals,
   const size_t smem = sizeof(TileSmem<A, R>);
   static bool configured[64] = {};
   if (!configured[st->device & 63]) {
-    B200_CUDA(cudaFuncSetAttribute(k_tile<A, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(k_tile<A, R, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(k_tile<A, R, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[st->device & 63] = true;
   }
   const uint64_t n_tiles = st->dim >> A;
@@ -567,8 +568,12 @@ static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals,
   // L2 prefetch of the next tile: measured no gain (the loads of a tile already overlap the other CTA's gates)
   // and ~2000 cycles per tile spent issuing 256 bulk prefetches; off unless B200_TILE_PREFETCH is set
   static const uint32_t flags = getenv("B200_TILE_PREFETCH") ? 1u : 0u;
-  k_tile<A, R, MINB><<<grid, NT, smem, st->stream>>>(st->amp, n_tiles, st->index_offset, d_desc, d_reals, d_cyc,
-                                                     flags | (init ? 2u : 0u), init_tile, init_local);
+  if (timing)
+    k_tile<A, R, MINB, true><<<grid, NT, smem, st->stream>>>(st->amp, n_tiles, st->index_offset, d_desc, d_reals, d_cyc,
+                                                             flags | (init ? 2u : 0u), init_tile, init_local);
+  else
+    k_tile<A, R, MINB, false><<<grid, NT, smem, st->stream>>>(st->amp, n_tiles, st->index_offset, d_desc, d_reals,
+                                                              nullptr, flags | (init ? 2u : 0u), init_tile, init_local);
   st->launches++;
   B200_CUDA(cudaGetLastError());
   if (timing) {
