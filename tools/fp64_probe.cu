@@ -25,6 +25,28 @@ __global__ void __launch_bounds__(256) k_dfma(double* out, int iters, double a, 
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// 16 DFMA + `MIX` x 16 integer ops per iteration, all independent: do integer instructions issue in the shadow of
+// the half-rate FP64 pipe, or does every DFMA hold the dispatch port for its two cycles?
+template <int MIX>
+__global__ void __launch_bounds__(256) k_mix(double* out, int iters, double a, double b, unsigned k) {
+  double c[16];
+  unsigned u[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { c[i] = threadIdx.x * 1e-9 + i; u[i] = threadIdx.x + i; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      c[i] = fma(c[i], a, b);
+#pragma unroll
+      for (int m = 0; m < MIX; ++m) u[i] = (u[i] ^ k) + (u[i] >> 3);
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += c[i] + u[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void __launch_bounds__(256) k_dmma(double* out, int iters, double a, double b) {
   double c[8][2];
 #pragma unroll
@@ -64,10 +86,23 @@ int main() {
     CHECK(cudaEventSynchronize(e1));
     CHECK(cudaEventElapsedTime(&ms_mma, e0, e1));
   }
+  float ms_mix1 = 0, ms_mix3 = 0;
+  CHECK(cudaEventRecord(e0));
+  k_mix<1><<<blocks, threads>>>(d, iters, 0.999999, 1e-9, 12345u);
+  CHECK(cudaEventRecord(e1));
+  CHECK(cudaEventSynchronize(e1));
+  CHECK(cudaEventElapsedTime(&ms_mix1, e0, e1));
+  CHECK(cudaEventRecord(e0));
+  k_mix<3><<<blocks, threads>>>(d, iters, 0.999999, 1e-9, 12345u);
+  CHECK(cudaEventRecord(e1));
+  CHECK(cudaEventSynchronize(e1));
+  CHECK(cudaEventElapsedTime(&ms_mix3, e0, e1));
   CHECK(cudaGetLastError());
   const double flops_fma = 2.0 * 16 * iters * (double)blocks * threads;
   const double flops_mma = 512.0 * 8 * iters * (double)blocks * (threads / 32);
-  printf("{\"device\": \"%s\", \"sms\": %d, \"dfma_tflops\": %.2f, \"dmma_m8n8k4_tflops\": %.2f, \"dfma_ms\": %.3f, \"dmma_ms\": %.3f}\n",
-         prop.name, prop.multiProcessorCount, flops_fma / ms_fma / 1e9, flops_mma / ms_mma / 1e9, ms_fma, ms_mma);
+  printf("{\"device\": \"%s\", \"sms\": %d, \"dfma_tflops\": %.2f, \"dmma_m8n8k4_tflops\": %.2f, \"dfma_ms\": %.3f, \"dmma_ms\": %.3f, "
+         "\"dfma_plus_3_int_ops_each_ms\": %.3f, \"dfma_plus_9_int_ops_each_ms\": %.3f}\n",
+         prop.name, prop.multiProcessorCount, flops_fma / ms_fma / 1e9, flops_mma / ms_mma / 1e9, ms_fma, ms_mma, ms_mix1,
+         ms_mix3);
   return 0;
 }
