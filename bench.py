@@ -240,7 +240,7 @@ def run_b200(args):
     cfg = None
     if args.tile_bits:
         from qaqarot_b200.planner import PlanConfig
-        cfg = PlanConfig(a=args.tile_bits, r=args.reg_bits)
+        cfg = PlanConfig(a=args.tile_bits, r=args.reg_bits, **({"max_cost": args.max_cost} if args.max_cost else {}))
     be = B200Backend(device=0, fusion=not args.no_fusion, plan_config=cfg)
     comp = be._compile(circ.ops, n, 0)
     prog = comp.prefix
@@ -494,6 +494,7 @@ def main():
     ap.add_argument("--no-fusion", action="store_true")
     ap.add_argument("--tile-bits", type=int, default=0, help="override the planner's tile size (log2 amplitudes)")
     ap.add_argument("--reg-bits", type=int, default=4, help="with --tile-bits: register bits per round (3 only with 11)")
+    ap.add_argument("--max-cost", type=float, default=0.0, help="with --tile-bits: planner's DFMA budget per amplitude per pass")
     ap.add_argument("--detail", default="", help="write per-op device times of the timed steps to this JSON file")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--nccl-exchange", action="store_true", help="sharded runs: exchange through NCCL send/recv instead of the peer-to-peer kernel")

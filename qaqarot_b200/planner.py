@@ -46,7 +46,9 @@ class PlanConfig:
     c: int = 4                # contiguous low bits always in the tile (2^c * 16 B rows)
     max_rounds: int = 6
     min_qubits: int = 9       # below this the state is tiny: one kernel per gate
-    max_cost: float = 150.0   # DFMA-equivalents per amplitude per pass before a new pass is opened
+    max_cost: float = 300.0   # DFMA-equivalents per amplitude per pass before a new pass is opened (a pass costs
+                              # ~7 ms of data movement at 30 qubits whatever it computes: measured 676 -> 645 ms
+                              # on the 30-qubit random-layer circuit going from 150 to 300)
     scan_limit: int = 4096    # how far ahead of the first unscheduled item a pass may look
     direct_io: bool = False   # let a first / last round bypass shared memory (measured neutral at A = 12: the
                               # loads and stores of a tile then stall the issuing warps instead of cp.async)
