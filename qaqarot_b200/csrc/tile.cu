@@ -255,7 +255,8 @@ struct RoundHdr {                  // 16 bytes
 template <int A, int R>
 struct TileSmem {
   c128 tile[1 << A];
-  c128 fix[kMaxFans];
+  c128 fix[2][kMaxFans];           // per-tile fan products, two generations: no barrier separates the last round of
+                                   // a tile from the head of the next one when that round stores straight to HBM
   uint64_t spread[kSpreadTabs][64];
   uint4 rec[kMaxGates + 1];
   double pay[kMaxPayload];         // the pass's matrices, phases and fan tables
@@ -372,7 +373,13 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
       tk0 = now;
     }
   };
-  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  // flags bit 2 (with a direct last round): the next tile's cp.async is issued as soon as every warp has taken
+  // the last round's amplitudes out of shared memory, so its HBM latency hides under that round's gates
+  const bool overlap = (flags & 4u) != 0 && direct_out && !direct_in && !init;
+  bool loaded = false;
+  uint32_t parity = 0;
+  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, parity ^= 1u) {
+    c128* const fixp = S.fix[parity];
     const uint64_t base = spread_tile(tile);
     const uint64_t fixedidx = base | index_offset;
     const uint32_t fx_lo = (uint32_t)fixedidx, fx_hi = (uint32_t)(fixedidx >> 32);
@@ -411,7 +418,7 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
       for (int i = 0; i < PER; ++i)
         *reinterpret_cast<c128*>(reinterpret_cast<unsigned char*>(sm) + (sw_t ^ (swz_c((uint32_t)i * NT) << 4))) =
             make_double2(0.0, 0.0);
-    } else {
+    } else if (!loaded) {
       uint64_t hb[R];
 #pragma unroll
       for (int k = 0; k < R; ++k) hb[k] = 1ull << byte_of(tb_lo, tb_hi, NTB + k);
@@ -443,7 +450,7 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
         q.y = __shfl_xor_sync(0xffffffffu, p.y, o);
         p = cmul(p, q);
       }
-      if (lane == 0) S.fix[f] = cmul(p, w[0]);
+      if (lane == 0) fixp[f] = cmul(p, w[0]);
     }
     tick(0);                      // issue: loads, fan setup
     if (!direct_in && !init) cp_async_wait_all();
@@ -471,6 +478,24 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
           v[i ^ (i >> 1)] = *reinterpret_cast<const c128*>(smb + s);
         }
       }
+      if (overlap && rd == n_rounds - 1) {
+        __syncthreads();          // every warp holds its amplitudes: the shared-memory tile is free
+        loaded = tile + gridDim.x < n_tiles;
+        if (loaded) {
+          const c128* __restrict__ gn = amp + spread_tile(tile + gridDim.x) + off_t;
+          uint64_t hb[R];
+#pragma unroll
+          for (int k = 0; k < R; ++k) hb[k] = 1ull << byte_of(tb_lo, tb_hi, NTB + k);
+#pragma unroll
+          for (int i = 0; i < PER; ++i) {
+            uint64_t off = 0;
+#pragma unroll
+            for (int k = 0; k < R; ++k)
+              if ((i >> k) & 1) off |= hb[k];
+            cp_async16(reinterpret_cast<unsigned char*>(sm) + (sw_t ^ (swz_c((uint32_t)i * NT) << 4)), gn + off);
+          }
+        }
+      }
       tick(2);                    // round: registers <- shared memory
       // the next record is fetched while the current one runs
       uint4 q = S.rec[first];
@@ -485,7 +510,7 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
           c128 wt = make_double2(1.0, 0.0);
           if ((key2 & 3u) == D_FANT || (key2 & 3u) == D_FAN) {
             const double2* __restrict__ tab = reinterpret_cast<const double2*>(pay_d);
-            wt = cmul(S.fix[(q.x >> 16) & 0xFFu], cmul(tab[lane], tab[32 + (NWARP_T > 1 ? warp : 0)]));
+            wt = cmul(fixp[(q.x >> 16) & 0xFFu], cmul(tab[lane], tab[32 + (NWARP_T > 1 ? warp : 0)]));
           }
           run_target<R>(v, key1, rm, S.pay + 2 * (q.z & 0xFFFFu));
           run_diag<R, NWARP_T>(v, key2, rm, pay_d, wt);
@@ -537,7 +562,7 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
     tick(6);                      // stream the tile back
     // the next tile's cp.async must not overwrite slots still being read (a direct first round writes shared
     // memory only after the barrier at the head of the next tile)
-    if (!(direct_in && direct_out)) __syncthreads();
+    if (!(direct_in && direct_out) && !overlap) __syncthreads();
     tick(7);                      // end-of-tile barrier
   }
 }
@@ -567,7 +592,7 @@ static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals,
   }
   // L2 prefetch of the next tile: measured no gain (the loads of a tile already overlap the other CTA's gates)
   // and ~2000 cycles per tile spent issuing 256 bulk prefetches; off unless B200_TILE_PREFETCH is set
-  static const uint32_t flags = getenv("B200_TILE_PREFETCH") ? 1u : 0u;
+  static const uint32_t flags = (getenv("B200_TILE_PREFETCH") ? 1u : 0u) | (getenv("B200_TILE_NO_OVERLAP") ? 0u : 4u);
   if (timing)
     k_tile<A, R, MINB, true><<<grid, NT, smem, st->stream>>>(st->amp, n_tiles, st->index_offset, d_desc, d_reals, d_cyc,
                                                              flags | (init ? 2u : 0u), init_tile, init_local);

@@ -50,8 +50,9 @@ class PlanConfig:
                               # ~7 ms of data movement at 30 qubits whatever it computes: measured 676 -> 645 ms
                               # on the 30-qubit random-layer circuit going from 150 to 300)
     scan_limit: int = 4096    # how far ahead of the first unscheduled item a pass may look
-    direct_io: bool = False   # let a first / last round bypass shared memory (measured neutral at A = 12: the
-                              # loads and stores of a tile then stall the issuing warps instead of cp.async)
+    direct_io: bool = False   # let the FIRST round load straight from HBM (measured neutral at A = 12)
+    direct_out: bool = True   # let the LAST round store straight to HBM when its register bits avoid the row bits:
+                              # the kernel then requests the next tile while that round's gates run
     kernel_tiles: Tuple[int, ...] = (9, 10, 11, 12, 13)   # tile sizes csrc/tile.cu instantiates (r = 4)
 
 
@@ -648,7 +649,8 @@ def _pack8(vals: Sequence[int]) -> Tuple[int, int]:
     return lo, hi
 
 
-def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int, direct_io: bool = False) -> None:
+def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int, direct_io: bool = False,
+                direct_out: bool = False) -> None:
     a = len(ps.tile)
     tile = ps.tile
     loc = {q: i for i, q in enumerate(tile)}
@@ -790,8 +792,10 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int, direct_io: bool
     def _direct(order):
         return c >= 3 and all(b >= c for b in order[:r]) and order[r:r + c] == list(range(c))
     flags = 0
-    if direct_io:
-        flags = (1 if _direct(encoded_rounds[0][0]) else 0) | (2 if _direct(encoded_rounds[-1][0]) else 0)
+    if direct_io and _direct(encoded_rounds[0][0]):
+        flags |= 1
+    if (direct_io or direct_out) and _direct(encoded_rounds[-1][0]):
+        flags |= 2
     words = [a | (c << 8) | (r << 16) | (len(ps.rounds) << 24) | (n_fans << 32) | (flags << 40), t_lo, t_hi,
              5 | (rounds_off << 32), pay_lo | (pay_len << 32)] + directory + body + round_words
     woff = prog.add_words(words)
@@ -871,7 +875,7 @@ def plan(prims: Sequence[Prim], n_qubits: int, cfg: PlanConfig = DEFAULT, n_loca
         ps, rest = build_pass(remaining, nl, a, r, c, cfg)
         if not ps.rounds:                                   # cannot happen: the head item always fits
             raise RuntimeError(f"planner made no progress at {remaining[0]}")
-        encode_pass(prog, ps, nl, r, c, cfg.direct_io)
+        encode_pass(prog, ps, nl, r, c, cfg.direct_io, cfg.direct_out)
         remaining = rest
     if sharded:
         prog.n_prims += norm.n_relabelled
