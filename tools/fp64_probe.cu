@@ -47,6 +47,19 @@ __global__ void __launch_bounds__(256) k_mix(double* out, int iters, double a, d
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// one dependent DFMA chain, one warp: cycles per DFMA = the FP64 pipeline latency seen by a lone warp
+__global__ void k_latency(double* out, long long* cycles, int iters, double a, double b) {
+  double c = threadIdx.x * 1e-9;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c = fma(c, a, b);
+  }
+  const long long t1 = clock64();
+  out[threadIdx.x] = c;
+  if (threadIdx.x == 0) cycles[0] = t1 - t0;
+}
+
 __global__ void __launch_bounds__(256) k_dmma(double* out, int iters, double a, double b) {
   double c[8][2];
 #pragma unroll
@@ -97,12 +110,19 @@ int main() {
   CHECK(cudaEventRecord(e1));
   CHECK(cudaEventSynchronize(e1));
   CHECK(cudaEventElapsedTime(&ms_mix3, e0, e1));
+  long long* d_cyc;
+  CHECK(cudaMalloc(&d_cyc, sizeof(long long)));
+  k_latency<<<1, 32>>>(d, d_cyc, 4096, 0.999999, 1e-9);
+  long long h_cyc = 0;
+  CHECK(cudaMemcpy(&h_cyc, d_cyc, sizeof h_cyc, cudaMemcpyDeviceToHost));
+  const double dfma_latency = (double)h_cyc / (4096.0 * 16);
   CHECK(cudaGetLastError());
   const double flops_fma = 2.0 * 16 * iters * (double)blocks * threads;
   const double flops_mma = 512.0 * 8 * iters * (double)blocks * (threads / 32);
   printf("{\"device\": \"%s\", \"sms\": %d, \"dfma_tflops\": %.2f, \"dmma_m8n8k4_tflops\": %.2f, \"dfma_ms\": %.3f, \"dmma_ms\": %.3f, "
-         "\"dfma_plus_3_int_ops_each_ms\": %.3f, \"dfma_plus_9_int_ops_each_ms\": %.3f}\n",
+         "\"dfma_plus_3_int_ops_each_ms\": %.3f, \"dfma_plus_9_int_ops_each_ms\": %.3f, "
+         "\"dfma_dependent_latency_cycles\": %.2f}\n",
          prop.name, prop.multiProcessorCount, flops_fma / ms_fma / 1e9, flops_mma / ms_mma / 1e9, ms_fma, ms_mma, ms_mix1,
-         ms_mix3);
+         ms_mix3, dfma_latency);
   return 0;
 }
