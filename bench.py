@@ -342,6 +342,7 @@ def run_b200(args):
         "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
         "config": {"workload": wl, "n_qubits": n, "gates": gates, "passes": prog.n_passes,
                    "state_bytes": int(16 * 2 ** n), "l2": "state larger than L2 (no flush needed)"},
+        "amp_updates_per_s": gates * 2.0 ** n / sec_per_step,
         "hbm_gbs": hbm_gbs, "hbm_frac_of_measured": hbm_gbs / peak,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "check": check,
@@ -471,7 +472,10 @@ def run_sharded(args, world: int):
             "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
             "config": {"workload": wl + f", sharded on the top {world.bit_length() - 1} index bits", "n_qubits": n,
                        "n_local": n_local, "gates": gates, "passes": prog.n_passes - prog.n_exchanges,
-                       "state_bytes_per_gpu": int(16 * 2 ** n_local), "l2": "shard larger than L2 (no flush needed)"},
+                       "state_bytes_per_gpu": int(16 * 2 ** n_local), "l2": "shard larger than L2 (no flush needed)",
+                       "scaling_note": "BASELINE.json names a different register per GPU count (30 q at 1, 33 q at 2 and "
+                                       "4, 36 q at 8), and gates/s falls with 2^n by construction: compare "
+                                       "amp_updates_per_s (= gates x 2^n / s) or hbm_gbs across N, not value"},
             "amp_updates_per_s": gates * 2.0 ** n / sec_per_step,
             "hbm_gbs": world * (prog.pass_bytes - 16.0 * 2 ** n_local * prog.n_exchanges) / sec_per_step / 1e9,
             "roofline": roofline, "exchange": exchange, "cpu_baseline": None, "e2e": e2e,
