@@ -242,7 +242,7 @@ def run_b200(args):
         from qaqarot_b200.planner import PlanConfig
         cfg = PlanConfig(a=args.tile_bits, r=args.reg_bits, **({"max_cost": args.max_cost} if args.max_cost else {}))
     be = B200Backend(device=0, fusion=not args.no_fusion, plan_config=cfg)
-    comp = be._compile(circ.ops, n, 0)
+    comp = be._compile(circ.ops, n, 0, from_zero=True)      # every step starts from |0...0>
     prog = comp.prefix
     st = be._state(n)
     st.set_profiling(True)
@@ -375,7 +375,7 @@ def run_sharded(args, world: int):
         from qaqarot_b200.planner import PlanConfig
         cfg = PlanConfig(a=args.tile_bits)
     be = ShardedB200Backend(device=local, plan_config=cfg)
-    comp = be._compile(circ.ops, n, 0)
+    comp = be._compile(circ.ops, n, 0, from_zero=True)
     prog = comp.prefix
     st = be._state(n)
     st.use_p2p = not args.nccl_exchange

@@ -63,10 +63,11 @@ class _Compiled:
     """Lowered + planned form of gates[start:], cached on the backend between runs of the same circuit."""
 
     def __init__(self, gates: Sequence, n_qubits: int, start: int, planner: Callable[..., Program],
-                 initial_layout: Optional[Sequence[int]] = None):
+                 initial_layout: Optional[Sequence[int]] = None, from_zero: bool = False):
         self.gates = tuple(gates)
         self.n_qubits = n_qubits
         self.start = start
+        self.from_zero = from_zero          # the prefix starts from |0...0>: its initial wire layout is free
         self.initial_layout = list(initial_layout) if initial_layout is not None else None
         low = lower(self.gates[start:], n_qubits, start)
         self.n_gates = low.n_gates
@@ -74,12 +75,17 @@ class _Compiled:
         user_planner = planner
         layout = [self.initial_layout]
 
+        first = [True]
+
         def planner(seg, n):            # a sharded planner leaves wires where they are: thread the layout along
+            free = from_zero and first[0] and getattr(user_planner, "accepts_free_layout", False)
+            first[0] = False
+            kw = {"free_initial_layout": True} if free else {}
             if getattr(user_planner, "threads_layout", False):
-                prog = user_planner(seg, n, layout[0])
+                prog = user_planner(seg, n, layout[0], **kw)
                 layout[0] = list(prog.final_pos)
                 return prog
-            return user_planner(seg, n)
+            return user_planner(seg, n, **kw)
 
         k = low.first_nonunitary if low.first_nonunitary is not None else len(prims)
         self.prefix_prims = prims[:k]
@@ -100,8 +106,9 @@ class _Compiled:
             self.rest.append(planner(seg, n_qubits))
         self.terminal = bool(self.rest) and all(isinstance(r, Prim) and r.kind == "measure" for r in self.rest)
 
-    def matches(self, gates: Sequence, n_qubits: int, start: int, initial_layout=None) -> bool:
+    def matches(self, gates: Sequence, n_qubits: int, start: int, initial_layout=None, from_zero=False) -> bool:
         return (n_qubits == self.n_qubits and start == self.start and len(gates) == len(self.gates)
+                and from_zero == self.from_zero
                 and (list(initial_layout) if initial_layout is not None else None) == self.initial_layout
                 and all(a is b for a, b in zip(gates, self.gates)))
 
@@ -128,11 +135,13 @@ class B200Backend(_Base):
         self.cache_idx = -1
         self._state_factory = state_factory or _default_state_factory
         if planner is None:
-            if fusion and plan_config is not None:
-                from .planner import plan as _plan
-                planner = lambda prims, n, _cfg=plan_config: _plan(prims, n, _cfg)
-            elif fusion:
-                from .planner import plan as planner
+            if fusion:
+                from .planner import DEFAULT, plan as _plan
+                _cfg = plan_config or DEFAULT
+
+                def planner(prims, n, free_initial_layout=False):
+                    return _plan(prims, n, _cfg, free_initial_layout=free_initial_layout)
+                planner.accepts_free_layout = True
             else:
                 planner = lambda prims, n: unfused_program(prims, n)
         self._planner = planner
@@ -175,10 +184,10 @@ class B200Backend(_Base):
             self._work = self._state_factory(n_qubits, self.device)
         return self._work
 
-    def _compile(self, gates: Sequence, n_qubits: int, start: int, initial_layout=None) -> _Compiled:
+    def _compile(self, gates: Sequence, n_qubits: int, start: int, initial_layout=None, from_zero=False) -> _Compiled:
         c = self._compiled
-        if c is None or not c.matches(gates, n_qubits, start, initial_layout):
-            c = self._compiled = _Compiled(gates, n_qubits, start, self._planner, initial_layout)
+        if c is None or not c.matches(gates, n_qubits, start, initial_layout, from_zero):
+            c = self._compiled = _Compiled(gates, n_qubits, start, self._planner, initial_layout, from_zero)
         return c
 
     def _download(self, st) -> np.ndarray:
@@ -194,7 +203,8 @@ class B200Backend(_Base):
         ctx = RunContext(n_qubits)
         cache, cache_idx = (self.cache, self.cache_idx) if use_backend_cache else (None, -1)
         start = cache_idx + 1 if cache is not None else 0
-        comp = self._compile(gates, n_qubits, start, getattr(cache, "layout", None) if cache is not None else None)
+        comp = self._compile(gates, n_qubits, start, getattr(cache, "layout", None) if cache is not None else None,
+                             from_zero=cache is None and initial is None)
         st = self._state(n_qubits)
         ctx.device_state = st
         if cache is not None:
@@ -466,9 +476,10 @@ class ShardedB200Backend(B200Backend):
         if device is None and host_state_factory is None:
             device = int(os.environ.get("LOCAL_RANK", "0"))
 
-        def planner(prims, n, layout=None):
-            return plan(prims, n, cfg, n_local=n - g, initial_pos=layout)
+        def planner(prims, n, layout=None, free_initial_layout=False):
+            return plan(prims, n, cfg, n_local=n - g, initial_pos=layout, free_initial_layout=free_initial_layout)
         planner.threads_layout = True
+        planner.accepts_free_layout = True
 
         def factory(n, dev):
             return ShardedState(n, device=dev, group=group, host_state_factory=host_state_factory)

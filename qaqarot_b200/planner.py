@@ -827,8 +827,22 @@ def _emit_single(prog: Program, it: Item, n: int) -> None:
     prog.n_prims += it.n_prims
 
 
+def cancelling_layout(prims: Sequence[Prim], n: int) -> List[int]:
+    """The wire -> index-bit layout to START from so that the relabelling done by the program's swap gates ends on
+    the identity (no restore pass).  Only meaningful when the initial state is |0...0>, which every layout
+    represents equally: a QFT then runs on a bit-reversed register and its final swaps cost nothing at all."""
+    perm = list(range(n))                       # perm[w]: the original position index now labelled w
+    for p in prims:
+        if p.kind == "swap":
+            perm[p.target], perm[p.aux] = perm[p.aux], perm[p.target]
+    pos0 = [0] * n
+    for w, v in enumerate(perm):                # final[w] = pos0[perm[w]] must equal w
+        pos0[v] = w
+    return pos0
+
+
 def plan(prims: Sequence[Prim], n_qubits: int, cfg: PlanConfig = DEFAULT, n_local: Optional[int] = None,
-         initial_pos: Optional[Sequence[int]] = None) -> Program:
+         initial_pos: Optional[Sequence[int]] = None, free_initial_layout: bool = False) -> Program:
     """Primitives of one unitary segment -> op program.
 
     Single GPU (n_local None): the program leaves every wire on its own index bit (relabelled swaps are paid back
@@ -838,6 +852,11 @@ def plan(prims: Sequence[Prim], n_qubits: int, cfg: PlanConfig = DEFAULT, n_loca
     n = n_qubits
     sharded = n_local is not None
     nl = n_local if sharded else n
+    if free_initial_layout and initial_pos is None and prims:
+        # the run starts from |0...0> (B200_OP_INIT): any layout is free, pick the one that cancels the swaps
+        pos0 = cancelling_layout(prims, n)
+        if pos0 != list(range(n)):
+            initial_pos = pos0
     prog = Program()
     prog.initial_pos = list(initial_pos) if initial_pos is not None else list(range(n))
     prog.final_pos = list(prog.initial_pos)

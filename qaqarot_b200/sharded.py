@@ -239,10 +239,14 @@ class ShardedState:
     # -- evolution --------------------------------------------------------------------------------
     def apply(self, program: Program, init_basis: Optional[int] = None) -> None:
         if init_basis is not None:
-            self.layout = list(range(self.n_qubits))
+            assert init_basis == 0, "only |0...0> is layout independent"
+            # |0...0> looks the same in every wire layout: adopt the one the program was planned from
+            self.layout = list(program.initial_pos) if program.initial_pos else list(range(self.n_qubits))
             segs = program.segments()
             if not segs or not isinstance(segs[0], Program):
+                layout = self.layout
                 self.set_basis(init_basis)
+                self.layout = layout
                 init_basis = None
         if len(program) == 0 and not program.final_pos:
             return

@@ -90,11 +90,34 @@ def test_restore_involutions_compose_to_the_permutation():
 def test_swaps_are_relabelled_not_executed():
     n = 10
     c = Circuit(n).h[:].swap[0, 7].cx[0, 3].rz(0.3)[7].swap[2, 7].h[2].cz[7, 1].swap[0, 1].swap[5, 6].swap[5, 6]
-    be = interp_backend(P.PlanConfig(a=9))
     ref = O.OracleBackend().run(c.ops, n)
+    # from |0...0> the planner starts on the layout that cancels the swaps: nothing is ever moved
+    be = interp_backend(P.PlanConfig(a=9))
     assert maxabs(c.run(backend=be), ref) <= TOL
     kinds = [o[0] for o in be._compiled.prefix._ops]
+    assert _lib.OP_SWAP not in kinds and _lib.OP_PERMUTE not in kinds
+    assert be._compiled.prefix.initial_pos != list(range(n)) and be._compiled.prefix.final_pos == list(range(n))
+    # from a caller-supplied state the layout is given: the swaps are paid back by in-place involutions at the end
+    rng = np.random.default_rng(3)
+    init = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
+    init /= np.linalg.norm(init)
+    be = interp_backend(P.PlanConfig(a=9))
+    assert maxabs(c.run(backend=be, initial=init), O.OracleBackend().run(c.ops, n, initial=init)) <= TOL
+    kinds = [o[0] for o in be._compiled.prefix._ops]
     assert _lib.OP_SWAP not in kinds and _lib.OP_PERMUTE in kinds
+
+
+def test_cancelling_layout_undoes_the_swap_relabelling():
+    rng = np.random.default_rng(9)
+    for n in (2, 5, 12):
+        c = Circuit(n)
+        for _ in range(15):
+            a, b = (int(x) for x in rng.choice(n, 2, replace=False))
+            c.swap[a, b].h[a]
+        low = lower(c.ops, n)
+        pos0 = P.cancelling_layout(low.prims, n)
+        norm = P.normalize(low.prims, n, initial_pos=pos0)
+        assert norm.final_pos == list(range(n))
 
 
 def test_one_qubit_chains_collapse():
