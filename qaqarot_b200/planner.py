@@ -874,7 +874,7 @@ def plan(prims: Sequence[Prim], n_qubits: int, cfg: PlanConfig = DEFAULT, n_loca
     if a not in cfg.kernel_tiles:
         a = max(t for t in cfg.kernel_tiles if t <= a)
     r = min(cfg.r, a)
-    c = min(cfg.c, a)
+    c = min(cfg.c, a if a == nl else a - 1)       # a tile smaller than the register needs at least one free bit
     remaining = list(norm.items)
     while remaining:
         head = remaining[0]
