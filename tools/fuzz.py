@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--gpu", action="store_true")
     ap.add_argument("--cases", type=int, default=200)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--shots", action="store_true", help="fuzz measurement: mid-circuit measure / reset, seeded shot Counters")
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
     all_tiles = tuple(range(1, 20))
@@ -48,6 +49,28 @@ def main():
                              max_cost=float(rng.choice([10, 150, 300])), max_rounds=int(rng.integers(1, 7)))
             be = B200Backend(state_factory=lambda nn, d: OracleState(nn, d), plan_config=cfg)
         ops = C.random_ops(rng, n, int(rng.integers(1, 200)), True)
+        if args.shots:
+            import random
+            ops = ops[:60]
+            for _ in range(int(rng.integers(0, 3))):          # mid-circuit measurements / resets
+                pos = int(rng.integers(0, len(ops) + 1))
+                ops.insert(pos, C._op("reset" if rng.integers(3) == 0 else "m", int(rng.integers(n))))
+            order = [int(q) for q in rng.permutation(n)[: int(rng.integers(1, n + 1))]]
+            ops.append(C._op("m", tuple(order) if len(order) > 1 else order[0]))
+            circ = C.build(Circuit, {"n": n, "ops": ops})
+            shots = int(rng.integers(1, 40))
+            seed = int(rng.integers(1 << 30))
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                random.seed(seed)
+                ref = O.OracleBackend().run(circ.ops, n, shots=shots)
+                random.seed(seed)
+                got = circ.run(backend=be, shots=shots)
+            be.close()
+            if got != ref:
+                print(f"SHOT MISMATCH case {k}: n={n} cfg={cfg} shots={shots} seed={seed}\n  got {dict(got)}\n  ref {dict(ref)}")
+                return 1
+            continue
         circ = C.build(Circuit, {"n": n, "ops": ops})
         init = None
         if rng.integers(2):
