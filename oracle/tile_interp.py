@@ -11,7 +11,8 @@ from __future__ import annotations
 import numpy as np
 
 T_NONE, T_MATC, T_MATR, T_X = 0, 1, 2, 3
-D_NONE, D_FANT, D_FAN, D_PHASE = 0, 1, 2, 3
+T_LAYER = 6
+D_NONE, D_FANT, D_FAN, D_PHASE, D_W, D_FIX, D_TAB = 0, 1, 2, 3, 4, 5, 6
 
 
 def _unpack8(lo: int, hi: int, count: int):
@@ -74,9 +75,27 @@ def run_tile_pass(psi: np.ndarray, n: int, words: np.ndarray, reals: np.ndarray,
             lm, rm = np.uint64((g0 >> 32) & 0xFFFF), np.uint64((g0 >> 48) & 0xFFFF)
             roff_t, roff_d = roffs & 0xFFFFFFFF, roffs >> 32
             cond = ((fixed & fm) == fm) & ((local & lm) == lm)
-            if tk != T_NONE:
-                assert j < r and dk in (D_NONE, D_FANT, D_FAN)
+            if tk == T_LAYER:
+                # up to one gate per register bit (reg mask says which), each as three shears; payload 4 x (z, x, y, 0)
+                assert int(fm) == 0 and int(lm) == 0 and 0 < int(rm) < (1 << r)
+                assert dk in (D_NONE, D_FANT, D_FAN, D_W, D_FIX, D_TAB)
+                pay = cplx(roff_t, 8)
+                for k in range(r):
+                    if not (int(rm) >> k) & 1:
+                        continue
+                    z, x, y = pay[2 * k].real, pay[2 * k].imag, pay[2 * k + 1].real
+                    tbit = np.uint64(1 << tile[order[k]])
+                    i0 = idx[(idx & tbit) == 0]
+                    i1 = i0 | tbit
+                    a0, a1 = psi[i0], psi[i1]
+                    a0 = a0 + z * a1
+                    a1 = a1 + x * a0
+                    a0 = a0 + y * a1
+                    psi[i0], psi[i1] = a0, a1
+            elif tk != T_NONE:
+                assert j < r and dk in (D_NONE, D_FANT, D_FAN, D_W, D_FIX)
                 assert dk == D_NONE or (int(fm) == 0 and int(lm) == 0), "a fused fan must be unconditional"
+                assert dk == D_NONE or (tk != T_X and int(rm) == 0), "only an uncontrolled 2x2 is fused with a fan"
                 c2 = cond & ((rho & rm) == rm)
                 tbit = np.uint64(1 << tile[order[j]])
                 i0 = idx[c2 & ((idx & tbit) == 0)]
@@ -85,6 +104,7 @@ def run_tile_pass(psi: np.ndarray, n: int, words: np.ndarray, reals: np.ndarray,
                 if tk == T_X:
                     psi[i0], psi[i1] = a1, a0
                 else:
+                    assert tk in (T_MATC, T_MATR)
                     m = cplx(roff_t, 4)
                     if tk == T_MATR:
                         assert np.all(m.imag == 0)
@@ -100,6 +120,16 @@ def run_tile_pass(psi: np.ndarray, n: int, words: np.ndarray, reals: np.ndarray,
                 if dk == D_FAN:
                     factor = factor * reg_t[rho.astype(np.int64)]
                 psi[keep] *= factor[keep]
+            elif dk in (D_W, D_FIX):
+                keep = cond if j >= r else cond & (((rho >> np.uint64(j)) & np.uint64(1)) == 1)
+                if dk == D_W:
+                    psi[keep] *= cplx(roff_d)[0]
+                else:
+                    psi[keep] *= fan_fixed[fid][keep]
+            elif dk == D_TAB:
+                assert int(fm) == 0 and int(lm) == 0, "a table applies to every amplitude"
+                tab = cplx(roff_d, 1 << r)
+                psi *= tab[rho.astype(np.int64)]
             elif dk == D_PHASE:
                 assert tk == T_NONE
                 keep = cond & ((rho & rm) == rm)

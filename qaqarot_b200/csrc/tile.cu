@@ -33,9 +33,16 @@
 //     A record runs where the fixed-bit mask (per tile) and the thread mask (per thread) are satisfied:
 //     target stage on register bit j:  1 = complex 2x2 (8 reals, row major re/im), 2 = real 2x2 (same layout),
 //                                      3 = pair swap; pairs whose other register bits satisfy reg_mask
+//                                      6 = layer: for each register bit k in reg_mask the three in-place shears
+//                                          a0 += z a1; a1 += x a0; a0 += y a1 on the pairs of bit k, payload
+//                                          4 x (z, x, y, 0); j unused.  A real 2x2 up to row scalings, which the
+//                                          planner keeps as a pending diagonal on the wire (planner.split_shears)
 //     diag stage:  1 / 2 = fan  amp *= fix[fan] * lane_t[lane] * warp_t[warp] (* reg_t[rho] for kind 2) on the
 //                  amplitudes with register bit j set (j = R: all); tables 32 + 2^(A-R-5) (+ 2^R) complex
 //                  3 = phase  amp *= reals[offset] where rho satisfies reg_mask (never fused with a target stage)
+//                  4 = fan without entries: amp *= reals[offset] on register bit j (a 1-qubit phase, no fan record)
+//                  5 = fan whose entries all lie outside the tile: amp *= fix[fan], no tables
+//                  6 = table: amp[rho] *= reals[offset + rho] (2^R complex), any diagonal on the register bits
 //     A 2x2 followed by a fan on the same register bit (the H + controlled-phase ladder of a QFT) is one record.
 #include "common.cuh"
 
@@ -45,8 +52,8 @@
 namespace b200 {
 
 constexpr int kMaxFans = 64;
-constexpr int T_NONE = 0, T_MATC = 1, T_MATR = 2, T_X = 3;
-constexpr int D_NONE = 0, D_FANT = 1, D_FAN = 2, D_PHASE = 3;
+constexpr int T_NONE = 0, T_MATC = 1, T_MATR = 2, T_X = 3, T_LAYER = 6;
+constexpr int D_NONE = 0, D_FANT = 1, D_FAN = 2, D_PHASE = 3, D_W = 4, D_FIX = 5, D_TAB = 6;
 
 __device__ __forceinline__ uint32_t swz(uint32_t l) {
   return l ^ ((l >> 3) & 7u) ^ ((l >> 6) & 7u) ^ ((l >> 9) & 7u) ^ ((l >> 12) & 7u);
@@ -191,21 +198,54 @@ __device__ __forceinline__ void fan_apply(c128 (&v)[1 << R], c128 wt, const doub
   }
 }
 
-// The two stages of a record are dispatched by two dense switches (one indirect branch each) on keys computed
-// once per CTA: a chain of `if (j == J)` / `if (kind == K)` tests cost ~15 dependent branches per record, which
-// two warps per scheduler cannot hide (clock64 phase timing: ~550 idle cycles per record in the gate phase).
-//   key1 = 8 j + target kind + 4 (register-bit controls present)      (0: no target stage)
-//   key2 = 4 j + diag kind, j = R for "every amplitude"               (0: no diag stage)
+// The two stages of a record are dispatched by two switches on keys computed once per CTA.  The compiler lowers
+// each switch to a compare tree, and tools/record_cost.py shows that the tree is what a record costs before it does
+// any arithmetic (~750 cycles per tile per CTA; one switch over all fused combinations was slower still), so the
+// two ops that carry most of the work of a layered circuit are tested first and do several gates per dispatch:
+//   LAYER  up to four 2x2 gates, one per register bit, each as three shears      (key1 = kKeyLayer)
+//   TAB    any diagonal on the register bits: amp[rho] *= table[rho]              (key2 = kKeyTab)
+//   key1 = 16 j + target kind + 8 (register-bit controls present)     (0: no target stage)
+//   key2 = 8 j + diag kind, j = 4 for "every amplitude"               (0: no diag stage)
+constexpr uint32_t kKeyLayer = 0xF0u, kKeyTab = 0xF1u;
+
+// (a0, a1) <- E(y) F(x) E(z) (a0, a1) on the pairs of register bit J, for the J in `mask`; payload 4 x (z, x, y, -)
+template <int R>
+__device__ __forceinline__ void layer_apply(c128 (&v)[1 << R], const double* __restrict__ pay, uint32_t mask) {
+#pragma unroll
+  for (int J = 0; J < R; ++J) {
+    if (!((mask >> J) & 1u)) continue;
+    const double z = pay[4 * J], x = pay[4 * J + 1], y = pay[4 * J + 2];
+#pragma unroll
+    for (int rho = 0; rho < (1 << R); ++rho) {
+      if (rho & (1 << J)) continue;
+      c128& a0 = v[rho];
+      c128& a1 = v[rho | (1 << J)];
+      asm("fma.rn.f64 %0, %4, %2, %0;\n\tfma.rn.f64 %1, %4, %3, %1;\n\t"
+          "fma.rn.f64 %2, %5, %0, %2;\n\tfma.rn.f64 %3, %5, %1, %3;\n\t"
+          "fma.rn.f64 %0, %6, %2, %0;\n\tfma.rn.f64 %1, %6, %3, %1;"
+          : "+d"(a0.x), "+d"(a0.y), "+d"(a1.x), "+d"(a1.y) : "d"(z), "d"(x), "d"(y));
+    }
+  }
+}
+template <int R>
+__device__ __forceinline__ void tab_apply(c128 (&v)[1 << R], const double2* __restrict__ tab) {
+#pragma unroll
+  for (int rho = 1; rho < (1 << R); ++rho) {
+    const double2 f = tab[rho];
+    amp_mul(v[rho], f.x, f.y, -f.y);
+  }
+}
+
 template <int R>
 __device__ __forceinline__ void run_target(c128 (&v)[1 << R], uint32_t key1, uint32_t rm, const double* __restrict__ pay) {
   switch (key1) {
 #define B200_T_CASES(J)                                                                           \
-    case 8 * J + T_MATC: mat_c<R, (J < R ? J : 0), false>(v, pay, 0); break;                        \
-    case 8 * J + T_MATR: mat_r<R, (J < R ? J : 0), false>(v, pay, 0); break;                        \
-    case 8 * J + T_X: perm_x<R, (J < R ? J : 0), false>(v, 0); break;                               \
-    case 8 * J + T_MATC + 4: mat_c<R, (J < R ? J : 0), true>(v, pay, rm); break;                    \
-    case 8 * J + T_MATR + 4: mat_r<R, (J < R ? J : 0), true>(v, pay, rm); break;                    \
-    case 8 * J + T_X + 4: perm_x<R, (J < R ? J : 0), true>(v, rm); break;
+    case 16 * J + T_MATC: mat_c<R, (J < R ? J : 0), false>(v, pay, 0); break;                       \
+    case 16 * J + T_MATR: mat_r<R, (J < R ? J : 0), false>(v, pay, 0); break;                       \
+    case 16 * J + T_X: perm_x<R, (J < R ? J : 0), false>(v, 0); break;                              \
+    case 16 * J + T_MATC + 8: mat_c<R, (J < R ? J : 0), true>(v, pay, rm); break;                   \
+    case 16 * J + T_MATR + 8: mat_r<R, (J < R ? J : 0), true>(v, pay, rm); break;                   \
+    case 16 * J + T_X + 8: perm_x<R, (J < R ? J : 0), true>(v, rm); break;
     B200_T_CASES(0) B200_T_CASES(1) B200_T_CASES(2) B200_T_CASES(3)
 #undef B200_T_CASES
     default: break;
@@ -217,11 +257,12 @@ __device__ __forceinline__ void run_diag(c128 (&v)[1 << R], uint32_t key2, uint3
   const double2* __restrict__ reg_t = reinterpret_cast<const double2*>(pay) + 32 + NWARP_T;
   switch (key2) {
 #define B200_D_CASES(J)                                                                           \
-    case 4 * J + D_FANT: fant_apply<R, (J < R ? J : R)>(v, wt); break;                              \
-    case 4 * J + D_FAN: fan_apply<R, (J < R ? J : R)>(v, wt, reg_t); break;
+    case 8 * J + D_FANT: case 8 * J + D_W: case 8 * J + D_FIX:                                      \
+      fant_apply<R, (J < R ? J : R)>(v, wt); break;                                                 \
+    case 8 * J + D_FAN: fan_apply<R, (J < R ? J : R)>(v, wt, reg_t); break;
     B200_D_CASES(0) B200_D_CASES(1) B200_D_CASES(2) B200_D_CASES(3) B200_D_CASES(4)
 #undef B200_D_CASES
-    case 4 * 4 + D_PHASE: {
+    case 8 * 4 + D_PHASE: {
       const double wx = pay[0], wy = pay[1];
 #pragma unroll
       for (int rho = 0; rho < (1 << R); ++rho)
@@ -240,7 +281,7 @@ constexpr int kMaxGates = 160;     // per pass
 constexpr int kMaxRounds = 8;
 constexpr int kSpreadTabs = 5;     // 6 bits of the tile number each: up to 30 non-tile index bits
 
-constexpr int kMaxPayload = 2048;  // float64 payload of one pass kept in shared memory (planner.MAX_PAYLOAD)
+constexpr int kMaxPayload = 2560;  // float64 payload of one pass kept in shared memory (planner.MAX_PAYLOAD)
 constexpr int kMaxFanWords = 512;  // directory + records of the pass's fans (planner keeps a pass below this)
 // record (one uint4): x = key1 | key2<<8 | fan<<16 | fixed mask bits 32..39<<24
 //                     y = thread mask | reg mask<<16    z = target payload | diag payload<<16 (complex units, relative)
@@ -340,8 +381,8 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
       const uint32_t pt = tk == T_NONE || tk == T_X ? 0u : (((uint32_t)roffs - pay_lo) >> 1);
       const uint32_t pd = dk == D_NONE ? 0u : (((uint32_t)(roffs >> 32) - pay_lo) >> 1);
       const uint32_t jj = j < (uint32_t)R ? j : 4u;            // 4 = no register target ("every amplitude")
-      const uint32_t key1 = tk == T_NONE ? 0u : 8u * jj + tk + (rm != 0 ? 4u : 0u);
-      const uint32_t key2 = dk == D_NONE ? 0u : 4u * jj + dk;
+      const uint32_t key1 = tk == T_NONE ? 0u : tk == T_LAYER ? kKeyLayer : 16u * jj + tk + (rm != 0 ? 8u : 0u);
+      const uint32_t key2 = dk == D_NONE ? 0u : dk == D_TAB ? kKeyTab : 8u * jj + dk;
       S.rec[first + gi] = make_uint4(key1 | (key2 << 8) | (fan << 16) | ((uint32_t)(fm >> 32) << 24),
                                      lm | (rm << 16), pt | (pd << 16), (uint32_t)fm);
     }
@@ -507,14 +548,25 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
         const bool active = ((fx_lo & q.w) == q.w) && ((fx_hi & fmh) == fmh) && ((lt & lm) == lm);
         if (active) {
           const uint32_t key1 = q.x & 0xFFu, key2 = (q.x >> 8) & 0xFFu;
+          const double* __restrict__ pay_t = S.pay + 2 * (q.z & 0xFFFFu);
           const double* __restrict__ pay_d = S.pay + 2 * (q.z >> 16);
-          c128 wt = make_double2(1.0, 0.0);
-          if ((key2 & 3u) == D_FANT || (key2 & 3u) == D_FAN) {
-            const double2* __restrict__ tab = reinterpret_cast<const double2*>(pay_d);
-            wt = cmul(fixp[(q.x >> 16) & 0xFFu], cmul(tab[lane], tab[32 + (NWARP_T > 1 ? warp : 0)]));
+          if (key1 == kKeyLayer) layer_apply<R>(v, pay_t, rm);       // (rm: which register bits carry a gate)
+          else if (key1 != 0u) run_target<R>(v, key1, rm, pay_t);
+          if (key2 == kKeyTab) {
+            tab_apply<R>(v, reinterpret_cast<const double2*>(pay_d));
+          } else if (key2 != 0u) {
+            const uint32_t dk = key2 & 7u;
+            c128 wt = make_double2(1.0, 0.0);
+            if (dk == D_FANT || dk == D_FAN) {
+              const double2* __restrict__ tab = reinterpret_cast<const double2*>(pay_d);
+              wt = cmul(fixp[(q.x >> 16) & 0xFFu], cmul(tab[lane], tab[32 + (NWARP_T > 1 ? warp : 0)]));
+            } else if (dk == D_FIX) {
+              wt = fixp[(q.x >> 16) & 0xFFu];
+            } else if (dk == D_W) {
+              wt = *reinterpret_cast<const double2*>(pay_d);             // the factor itself
+            }
+            run_diag<R, NWARP_T>(v, key2, rm, pay_d, wt);
           }
-          run_target<R>(v, key1, rm, S.pay + 2 * (q.z & 0xFFFFu));
-          run_diag<R, NWARP_T>(v, key2, rm, pay_d, wt);
         }
         q = nq;
       }

@@ -32,9 +32,12 @@ from .lowering import Prim
 from .program import Program
 
 T_NONE, T_MATC, T_MATR, T_X = 0, 1, 2, 3          # target stage of a tile gate record
+T_LAYER = 6                                         # ... up to one 3-shear gate per register bit (reg_mask says which)
 D_NONE, D_FANT, D_FAN, D_PHASE = 0, 1, 2, 3         # diagonal stage (fan without / with register table, phase)
+D_W, D_FIX = 4, 5                                   # ... fan without entries / with entries outside the tile only
+D_TAB = 6                                           # ... one factor per register amplitude
 MAX_GATES = 160          # per pass (record slots in csrc/tile.cu)
-MAX_PAYLOAD = 2048       # float64 payload of one pass (shared-memory copy in csrc/tile.cu)
+MAX_PAYLOAD = 2560       # float64 payload of one pass (shared-memory copy in csrc/tile.cu)
 MAX_FAN_WORDS = 512      # fan directory + records of one pass (shared-memory copy in csrc/tile.cu)
 MAX_FANS = 64            # per pass (shared-memory slots in csrc/tile.cu)
 
@@ -54,6 +57,8 @@ class PlanConfig:
     direct_out: bool = True   # let the LAST round store straight to HBM when its register bits avoid the row bits:
                               # the kernel then requests the next tile while that round's gates run
     kernel_tiles: Tuple[int, ...] = (9, 10, 11, 12, 13)   # tile sizes csrc/tile.cu instantiates (r = 4)
+    shears: bool = True       # 1-qubit gates as phase . rotation by three shears . phase (split_shears), and
+                              # CX as H . CZ . H
 
 
 DEFAULT = PlanConfig()
@@ -61,7 +66,7 @@ DEFAULT = PlanConfig()
 
 class Item:
     """One schedulable unit after normalisation."""
-    __slots__ = ("kind", "t", "ctrls", "m", "bits", "w", "entries", "aux", "nd", "dg", "n_prims", "pos")
+    __slots__ = ("kind", "t", "ctrls", "m", "bits", "w", "entries", "aux", "nd", "dg", "n_prims", "pos", "sh")
 
     def __init__(self, kind, t=-1, ctrls=(), m=None, bits=(), w=1.0 + 0j, entries=None, aux=-1, n_prims=1):
         self.kind = kind            # mat | x | phase | fan | swap
@@ -74,6 +79,7 @@ class Item:
         self.aux = aux              # swap: second qubit
         self.n_prims = n_prims
         self.pos = -1
+        self.sh = None              # mat: (z, x, y) when m = shear_matrix(z, x, y) is applied as three shears
         self.refresh()
 
     def refresh(self):
@@ -105,6 +111,7 @@ class Item:
 # ---------------------------------------------------------------------------------------------------------
 _ID = np.array([1, 0, 0, 1], dtype=complex)
 _XM = np.array([0, 1, 1, 0], dtype=complex)
+_HM = np.array([1, 1, 1, -1], dtype=complex) / np.sqrt(2.0)
 
 
 def _mul(a: np.ndarray, b: np.ndarray) -> np.ndarray:
@@ -127,6 +134,55 @@ def _as_matrix(p: Prim) -> np.ndarray:
     if p.kind == "diag":
         return np.array([p.data[0], 0, 0, p.data[1]], dtype=complex)
     return _XM
+
+
+def _unit(z: complex) -> complex:
+    return z / abs(z)
+
+
+def shear_matrix(z: float, x: float, y: float) -> np.ndarray:
+    """The real 2x2 (row major) that the three in-place shears of a LAYER record apply to a pair (a0, a1)
+    (csrc/tile.cu):  a0 += z a1;  a1 += x a0;  a0 += y a1."""
+    return np.array([1.0 + x * y, z + y * (1.0 + x * z), x, 1.0 + x * z], dtype=complex)
+
+
+def split_shears(m) -> Optional[Tuple[complex, complex, float, float, float, complex]]:
+    """A 2x2 unitary as
+
+        m = g * diag(1, dl) . R(theta) . diag(1, dr),     |g| = |dl| = |dr| = 1,  |theta| <= pi/2,
+
+    with the rotation R(theta) = [[cos, -sin], [sin, cos]] applied as three shears (the lifting scheme)
+    z = y = -tan(theta / 2), x = sin(theta): 3 FMAs per component of an amplitude pair, in place, no temporaries --
+    against 8 multiply-adds and a copy for a complex 2x2.  `dr` joins the phases in front of the gate, `g` the
+    segment's global factor, and `dl` stays on the wire as a pending phase (it commutes with every control and
+    phase and is absorbed by the next gate on the wire).  A real rotation keeps dl = dr = 1; a real reflection
+    (H) is a rotation times Z, dl = -1.
+    Returns (g, dl, z, x, y, dr), or None when the pieces do not reproduce `m` to rounding (not unitary)."""
+    m = np.asarray(m, dtype=complex).reshape(4)
+    if not np.all(np.isfinite(m)):
+        return None
+    a, b, c, d = (complex(v) for v in m)
+    if c == 0 or b == 0:
+        return None                               # diagonal matrices never get here; anything else is not unitary
+    if np.all(m.imag == 0):
+        det = a.real * d.real - b.real * c.real
+        dl = 1.0 + 0j if det > 0 else -1.0 + 0j   # m = diag(1, dl) . R
+        theta = np.arctan2(c.real * dl.real, a.real)
+        g, dr = 1.0 + 0j, 1.0 + 0j
+        if abs(theta) > np.pi / 2:                 # R(theta) = -R(theta -+ pi)
+            theta -= np.copysign(np.pi, theta)
+            g = -1.0 + 0j
+    else:
+        theta = np.arctan2(abs(c), abs(a))         # in [0, pi/2]
+        g = _unit(a) if a != 0 else 1.0 + 0j
+        dl = _unit(c) / g
+        dr = -_unit(b) / g
+    z, x = -np.tan(theta / 2.0), np.sin(theta)
+    sm = shear_matrix(z, x, z)
+    rec = g * np.array([sm[0], sm[1] * dr, dl * sm[2], dl * sm[3] * dr])
+    if np.max(np.abs(rec - m)) > 2e-15:
+        return None
+    return g, dl, float(z), float(x), float(z), dr
 
 
 def fold_conjugated_phases(prims: Sequence[Prim]) -> List[Prim]:
@@ -236,7 +292,7 @@ class Normalized:
 
 def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = True,
               relabel_swaps: bool = True, n_local: Optional[int] = None,
-              initial_pos: Optional[Sequence[int]] = None) -> Normalized:
+              initial_pos: Optional[Sequence[int]] = None, shears: bool = False) -> Normalized:
     """`n_local` < n: the state is sharded on its top n - n_local index bits (one shard per GPU).  A gate that is
     non-diagonal on a wire living on such a *global* bit first brings the wire home: the global bit is exchanged
     with the top local bit (an `exchange` item: half of every shard crosses NVLink), after a local transposition
@@ -324,7 +380,10 @@ def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = 
                 return
         emit_phase(bits, w, count)
 
-    def flush(q: int):
+    def flush(q: int, keep_diag: bool = False):
+        """Emit the pending 2x2 of index bit q.  With `shears` a non-diagonal one leaves a phase behind;
+        `keep_diag` lets it stay pending (the caller only needs the wire diagonal, e.g. before using it as a
+        control), otherwise it follows at once."""
         m, cnt = pending[q], pending_count[q]
         pending[q], pending_count[q] = None, 0
         if m is None:
@@ -338,8 +397,22 @@ def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = 
             return
         if np.array_equal(m, _XM):
             push(Item("x", t=q, n_prims=cnt), last_touch[q])
-        else:
+            return
+        sp = split_shears(m) if shears else None
+        if sp is None:
             push(Item("mat", t=q, m=m, n_prims=cnt), last_touch[q])
+            return
+        g, dl, z, x, y, dr = sp
+        scalar[0] *= g
+        emit_phase((q,), dr, 0, early=True)
+        it = Item("mat", t=q, m=shear_matrix(z, x, y), n_prims=cnt)
+        it.sh = (z, x, y)
+        push(it, last_touch[q])
+        if keep_diag:
+            if dl != 1.0:
+                pending[q] = np.array([1.0, 0.0, 0.0, dl], dtype=complex)
+        else:
+            emit_phase((q,), dl, 0, early=True)
 
     prims = fold_conjugated_phases(prims)
     pos = list(initial_pos) if initial_pos is not None else list(range(n))   # wire -> index bit of its data
@@ -377,7 +450,7 @@ def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = 
         # a pending non-diagonal 2x2 must be applied while its wire is still local
         for q in (best, top):
             if pending[q] is not None and not _is_diag(pending[q]):
-                flush(q)
+                flush(q, keep_diag=True)
         if best != top:
             push(Item("perm", t=best, aux=top, n_prims=0))
             move(best, top)
@@ -390,7 +463,7 @@ def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = 
         if p.kind == "exchange":                  # from shard_schedule: wire p.target comes home, p.aux leaves
             gpos, lbit = pos[p.target], pos[p.aux]
             if pending[lbit] is not None and not _is_diag(pending[lbit]):
-                flush(lbit)                       # a non-diagonal 2x2 must be applied while its wire is local
+                flush(lbit, keep_diag=True)       # a non-diagonal 2x2 must be applied while its wire is local
             push(Item("exchange", t=lbit, aux=gpos, n_prims=0))
             move(lbit, gpos)
             out.n_exchanges += 1
@@ -438,17 +511,29 @@ def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = 
             for q in qubits:
                 m = pending[q]
                 if m is not None and not _is_diag(m) and not _is_antidiag(m):
-                    flush(q)
+                    flush(q, keep_diag=True)
             if d0 == 1.0:
                 emit_conjugated(qubits, d1, 1)
             else:
                 emit_conjugated(ctrls, d0, 1)
                 emit_conjugated(qubits, d1 / d0, 0)
             continue
+        if shears and p.kind == "x" and len(ctrls) == 1:
+            # CX = H_t . CZ . H_t: the Hadamards merge into the 1-qubit gates around them, and the CZ is a phase
+            # (a table entry or a fan entry) instead of 2^R amplitude moves per thread
+            pending[tgt] = _HM if pending[tgt] is None else _mul(_HM, pending[tgt])
+            pending_count[tgt] += 1
+            for q in (ctrls[0], tgt):
+                m = pending[q]
+                if m is not None and not _is_diag(m) and not _is_antidiag(m):
+                    flush(q, keep_diag=True)
+            emit_conjugated((ctrls[0], tgt), -1.0 + 0j, 0)
+            pending[tgt] = _HM if pending[tgt] is None else _mul(_HM, pending[tgt])
+            continue
         for cq in ctrls:
             m = pending[cq]
             if m is not None and not _is_diag(m):
-                flush(cq)
+                flush(cq, keep_diag=True)
         flush(tgt)
         if p.kind == "x":
             push(Item("x", t=tgt, ctrls=ctrls))
@@ -503,6 +588,8 @@ def restore_involutions(final_pos: Sequence[int]) -> List[List[Tuple[int, int]]]
 def _cost(it: Item) -> float:
     """Rough DFMA-equivalents per amplitude."""
     if it.kind == "mat":
+        if it.sh is not None:
+            return 3.0
         base = 4.0 if np.all(np.asarray(it.m).imag == 0) else 8.0
         return base / (1 << len(it.ctrls))
     if it.kind == "x":
@@ -510,17 +597,19 @@ def _cost(it: Item) -> float:
     if it.kind == "phase":
         return 4.0 / (1 << len(it.bits))
     if it.kind == "fan":
-        return 5.0
+        return 5.0 if it.entries else 3.0
     return 0.0
 
 
 def _payload(it: Item, a: int, r: int) -> int:
     """Upper bound of the float64 payload an item adds to its pass."""
     if it.kind == "mat":
-        return 8
+        return 8 if it.sh is None else 48          # a layer record (16) and its table (32), if it opens a new one
     if it.kind == "phase":
         return 4
     if it.kind == "fan":
+        if not it.entries:
+            return 2
         return 2 * (2 + len(it.entries) + 32 + (1 << max(0, a - r - 5)) + 2 * (1 << r))
     return 0
 
@@ -569,8 +658,9 @@ def build_pass(remaining: List[Item], n: int, a: int, r: int, c: int, cfg: PlanC
             it = remaining[idx]
             ok = it.kind not in ("swap", "perm", "exchange") and not _conflict(it, skipped_nd, skipped_dg)
             pay = _payload(it, a, r)
-            fw = 3 + len(it.entries) if it.kind == "fan" else (1 if it.kind == "phase" else 0)
-            if ok and ((it.kind == "fan" and n_fans >= MAX_FANS - 1) or n_gates + 2 >= MAX_GATES - 1
+            is_fan = it.kind == "fan" and bool(it.entries)
+            fw = 3 + len(it.entries) if is_fan else (1 if it.kind in ("phase", "fan") else 0)
+            if ok and ((is_fan and n_fans >= MAX_FANS - 1) or n_gates + 2 >= MAX_GATES - 1
                        or payload + pay > MAX_PAYLOAD - 64 or fan_words + fw > MAX_FAN_WORDS - 8):
                 ok = False
             if ok and it.nd:
@@ -587,7 +677,7 @@ def build_pass(remaining: List[Item], n: int, a: int, r: int, c: int, cfg: PlanC
             if ok:
                 picked.append(idx)
                 cost += _cost(it)
-                n_fans += it.kind == "fan"
+                n_fans += is_fan
                 n_gates += 2 if it.kind == "fan" else 1
                 payload += pay
                 fan_words += fw
@@ -649,6 +739,55 @@ def _pack8(vals: Sequence[int]) -> Tuple[int, int]:
     return lo, hi
 
 
+class _Group:
+    """One LAYER / TAB record being assembled by encode_pass: up to one shear gate per register bit, then one
+    factor per register amplitude (any diagonal on the register bits), or instead of it one fan (`diag`).
+    Items joining the group after other records were emitted are hoisted in front of those, hence the `blocked`
+    sets: register bits on which a shear (`blocked_sh`) or a diagonal (`blocked_dg`) may no longer join."""
+
+    def __init__(self, r: int):
+        self.r = r
+        self.sh: Dict[int, Tuple[float, float, float]] = {}     # register bit -> (z, x, y)
+        self.tab = np.ones(1 << r, dtype=complex)
+        self.has_tab = False
+        self.diag: Optional[dict] = None
+        self.clean = True                                        # no foreign record since the group opened
+        self.blocked_sh: set = set()
+        self.blocked_dg: set = set()
+
+    def mul_phase(self, regs, w: complex) -> None:
+        mask = sum(1 << k for k in regs)
+        for rho in range(1 << self.r):
+            if rho & mask == mask:
+                self.tab[rho] *= w
+        self.has_tab = True
+
+    def mul_fan(self, kt: int, w0: complex, entries: Dict[int, complex]) -> None:
+        for rho in range(1 << self.r):
+            if (rho >> kt) & 1:
+                f = complex(w0)
+                for k, w in entries.items():
+                    if (rho >> k) & 1:
+                        f *= w
+                self.tab[rho] *= f
+        self.has_tab = True
+
+    def words_kw(self, prog: Program, r: int) -> Optional[dict]:
+        kw: dict = {}
+        if self.sh:
+            pay: List[complex] = []
+            for k in range(4):
+                z, x, y = self.sh.get(k, (0.0, 0.0, 0.0))
+                pay += [complex(z, x), complex(y, 0.0)]
+            kw = dict(tk=T_LAYER, rm=sum(1 << k for k in self.sh), roff_t=prog.add_reals(pay))
+        if self.has_tab:
+            assert self.diag is None
+            kw.update(dk=D_TAB, roff_d=prog.add_reals(list(self.tab)))
+        elif self.diag is not None:
+            kw.update(j=self.diag["j"], dk=self.diag["dk"], fid=self.diag["fid"], roff_d=self.diag["roff_d"])
+        return kw or None
+
+
 def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int, direct_io: bool = False,
                 direct_out: bool = False) -> None:
     a = len(ps.tile)
@@ -681,6 +820,9 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int, direct_io: bool
         j = r if j is None else j
         return [tk | (j << 8) | (dk << 16) | (fid << 24) | (lm << 32) | (rm << 48), fm, roff_t | (roff_d << 32)]
 
+    def gate_words_kw(**kw) -> dict:
+        return kw
+
     def fan_fields(order, fid_entries, w0, lw, tgt) -> dict:
         """One fan: fixed (mask, w) entries, local per-bit factors `lw`, optional target qubit -> gate fields."""
         fid = len(fan_records)
@@ -695,8 +837,12 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int, direct_io: bool
                     lm = 1 << loc[tgt]
             else:
                 fm = 1 << tgt
+        if not fid_entries and not lw and tgt is not None:        # a 1-qubit phase: the factor is the payload
+            return dict(j=jreg, dk=D_W, fid=0, lm=lm, fm=fm, roff_d=prog.add_reals([w0]))
         fr_off = prog.add_reals([w0] + [w for _, w in fid_entries])
         fan_records.append([len(fid_entries) | (fr_off << 32)] + [m for m, _ in fid_entries])
+        if not lw:                                                # constant over a tile: no tables
+            return dict(j=jreg, dk=D_FIX, fid=fid, lm=lm, fm=fm, roff_d=fr_off)
         tbits = order[r:]
         lane_t = np.ones(32, dtype=complex)
         for x in range(32):
@@ -721,17 +867,50 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int, direct_io: bool
     encoded_rounds: List[Tuple[List[int], List[int]]] = []
     for rd in ps.rounds:
         order = _thread_order(tile, rd.reg)
-        gates: List[int] = []
+        out: List[object] = []                    # gate_words keyword dicts and _Group objects, in execution order
         pending_t: Optional[dict] = None          # target stage waiting for a fan on the same register bit
+        grp: Optional[_Group] = None              # open layer / table record (see _Group)
 
         def flush_t():
             nonlocal pending_t
             if pending_t is not None:
-                gates.extend(gate_words(**pending_t))
+                out.append(pending_t)
                 pending_t = None
+
+        def reg_index(q) -> Optional[int]:
+            li = loc.get(q)
+            if li is None:
+                return None
+            k = order.index(li)
+            return k if k < r else None
+
+        def foreign(kw: dict, nd_bits, dg_bits):
+            """A record of its own after the open group: later gates may join the group only if they commute with it."""
+            out.append(kw)
+            if grp is not None:
+                grp.clean = False
+                for q in nd_bits:
+                    k = reg_index(q)
+                    if k is not None:
+                        grp.blocked_sh.add(k)
+                        grp.blocked_dg.add(k)
+                for q in dg_bits:
+                    k = reg_index(q)
+                    if k is not None:
+                        grp.blocked_sh.add(k)
 
         for it in rd.items:
             n_prims += it.n_prims
+            if it.kind == "mat" and it.sh is not None:
+                flush_t()
+                k = reg_index(it.t)
+                assert k is not None and not it.ctrls, "non-diagonal target outside the round's register bits"
+                if grp is None or k in grp.blocked_sh:
+                    grp = _Group(r)
+                    out.append(grp)
+                grp.sh[k] = it.sh
+                grp.blocked_sh.add(k)
+                continue
             if it.kind in ("mat", "x"):
                 flush_t()
                 j = order.index(loc[it.t])
@@ -739,33 +918,75 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int, direct_io: bool
                 lm, rm, fm = split_mask(it.ctrls, order)
                 if it.kind == "mat":
                     real = bool(np.all(np.asarray(it.m).imag == 0))
-                    pending_t = dict(tk=T_MATR if real else T_MATC, j=j, lm=lm, rm=rm, fm=fm, roff_t=prog.add_reals(it.m))
+                    kw = dict(tk=T_MATR if real else T_MATC, j=j, lm=lm, rm=rm, fm=fm, roff_t=prog.add_reals(it.m))
                 else:
-                    pending_t = dict(tk=T_X, j=j, lm=lm, rm=rm, fm=fm)
-            elif it.kind == "phase":
-                if not any(q in loc for q in it.bits):
+                    kw = dict(tk=T_X, j=j, lm=lm, rm=rm, fm=fm)
+                if grp is not None:
+                    foreign({}, (it.t,), it.ctrls)
+                    out.pop()
+                pending_t = kw
+                continue
+            # ---- diagonal items ------------------------------------------------------------------------------
+            bits = it.bits if it.kind == "phase" else (it.t,) + tuple(it.entries)
+            if not any(q in loc for q in bits):
+                if it.kind == "phase":
                     scalars.append((sum(1 << q for q in it.bits), it.w))
-                    continue
-                flush_t()
-                lm, rm, fm = split_mask(it.bits, order)
-                gates += gate_words(dk=D_PHASE, lm=lm, rm=rm, fm=fm, roff_d=prog.add_reals([it.w]))
-            else:                                           # fan
-                if it.t not in loc and not any(q in loc for q in it.entries):
+                else:
                     scalars.append((1 << it.t, it.w))
                     scalars += [((1 << it.t) | (1 << q), w) for q, w in it.entries.items()]
-                    continue
-                fixed = [(1 << q, w) for q, w in it.entries.items() if q not in loc]
-                lw = {loc[q]: w for q, w in it.entries.items() if q in loc}
-                f = fan_fields(order, fixed, it.w, lw, it.t)
-                if (pending_t is not None and pending_t["j"] == f["j"] and f["j"] < r and pending_t["lm"] == 0
-                        and pending_t["fm"] == 0):
-                    # 2x2 on a register bit followed by a fan on the same bit: one record, one dispatch
-                    pending_t.update(dk=f["dk"], fid=f["fid"], roff_d=f["roff_d"])
-                    flush_t()
+                continue
+            regs = [reg_index(q) for q in bits]
+            if all(k is not None for k in regs) and pending_t is None:
+                # purely on register bits: one factor per register amplitude, shared by every thread
+                if grp is None or grp.diag is not None or (set(regs) & grp.blocked_dg):
+                    grp = _Group(r)
+                    out.append(grp)
+                if it.kind == "phase":
+                    grp.mul_phase(regs, it.w)
                 else:
-                    flush_t()
-                    gates += gate_words(**f)
+                    grp.mul_fan(regs[0], it.w, {reg_index(q): w for q, w in it.entries.items()})
+                grp.blocked_sh |= set(regs)
+                continue
+            if it.kind == "phase":
+                flush_t()
+                lm, rm, fm = split_mask(it.bits, order)
+                foreign(gate_words_kw(dk=D_PHASE, lm=lm, rm=rm, fm=fm, roff_d=prog.add_reals([it.w])), (), bits)
+                continue
+            kt = reg_index(it.t)
+            can_fuse = (pending_t is None and grp is not None and grp.clean and grp.sh and not grp.has_tab
+                        and grp.diag is None and kt is not None)
+            entries, w0 = dict(it.entries), it.w
+            if (not can_fuse and pending_t is None and grp is not None and grp.diag is None and kt is not None
+                    and kt not in grp.blocked_dg):
+                # the factors between register bits go into the group's table, the rest stays a fan
+                reg_part = {reg_index(q): w for q, w in entries.items() if reg_index(q) is not None}
+                if reg_part and not (set(reg_part) & grp.blocked_dg):
+                    grp.mul_fan(kt, 1.0 + 0j, reg_part)
+                    grp.blocked_sh |= set(reg_part) | {kt}
+                    entries = {q: w for q, w in entries.items() if reg_index(q) is None}
+            fixed = [(1 << q, w) for q, w in entries.items() if q not in loc]
+            lw = {loc[q]: w for q, w in entries.items() if q in loc}
+            f = fan_fields(order, fixed, w0, lw, it.t)
+            if can_fuse:
+                grp.diag = f
+                grp.blocked_sh |= {k for k in regs if k is not None}
+            elif (pending_t is not None and pending_t["j"] == f["j"] and f["j"] < r and pending_t["lm"] == 0
+                    and pending_t["fm"] == 0 and pending_t["rm"] == 0 and pending_t["tk"] != T_X):
+                # 2x2 on a register bit followed by a fan on the same bit: one record, one dispatch
+                pending_t.update(dk=f["dk"], fid=f["fid"], roff_d=f["roff_d"])
+                flush_t()
+                if grp is not None:
+                    foreign({}, (), bits)
+                    out.pop()
+            else:
+                flush_t()
+                foreign(f, (), bits)
         flush_t()
+        gates: List[int] = []
+        for e in out:
+            kw = e.words_kw(prog, r) if isinstance(e, _Group) else e
+            if kw:
+                gates += gate_words(**kw)
         encoded_rounds.append((order, gates))
     if scalars:
         order, gates = encoded_rounds[-1]
@@ -862,7 +1083,8 @@ def plan(prims: Sequence[Prim], n_qubits: int, cfg: PlanConfig = DEFAULT, n_loca
     prog.final_pos = list(prog.initial_pos)
     if not prims:
         return prog
-    norm = normalize(prims, n, n_local=nl, initial_pos=initial_pos)
+    norm = normalize(prims, n, n_local=nl, initial_pos=initial_pos,
+                     shears=cfg.shears and (sharded or n >= cfg.min_qubits))
     prog.final_pos = list(norm.final_pos)
     if not sharded and n < cfg.min_qubits:
         for it in norm.items:
