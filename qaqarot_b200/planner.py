@@ -175,8 +175,9 @@ def split_shears(m) -> Optional[Tuple[complex, complex, float, float, float, com
     else:
         theta = np.arctan2(abs(c), abs(a))         # in [0, pi/2]
         g = _unit(a) if a != 0 else 1.0 + 0j
-        dl = _unit(c) / g
         dr = -_unit(b) / g
+        # the phases are read off the LARGE entries (those of small ones are only known to ~eps / |entry|)
+        dl = _unit(d) / (g * dr) if abs(a) >= abs(c) else _unit(c) / g
     z, x = -np.tan(theta / 2.0), np.sin(theta)
     sm = shear_matrix(z, x, z)
     rec = g * np.array([sm[0], sm[1] * dr, dl * sm[2], dl * sm[3] * dr])
@@ -636,8 +637,14 @@ def _conflict(it: Item, skipped_nd: set, skipped_dg: set) -> bool:
     return False
 
 
-def build_pass(remaining: List[Item], n: int, a: int, r: int, c: int, cfg: PlanConfig) -> Tuple[Pass, List[Item]]:
-    """Greedy: returns the pass and the items left over (program order preserved)."""
+class PassOverflow(Exception):
+    """The encoded pass does not fit the kernel's per-pass shared-memory tables."""
+
+
+def build_pass(remaining: List[Item], n: int, a: int, r: int, c: int, cfg: PlanConfig,
+               pay_scale: float = 1.0) -> Tuple[Pass, List[Item]]:
+    """Greedy: returns the pass and the items left over (program order preserved).  `pay_scale` < 1 trusts that
+    the encoder will need less payload than the per-item upper bounds (most fans end up as table entries)."""
     tile = set(range(c))
     rounds: List[Round] = []
     done = [False] * len(remaining)
@@ -657,7 +664,7 @@ def build_pass(remaining: List[Item], n: int, a: int, r: int, c: int, cfg: PlanC
                 continue
             it = remaining[idx]
             ok = it.kind not in ("swap", "perm", "exchange") and not _conflict(it, skipped_nd, skipped_dg)
-            pay = _payload(it, a, r)
+            pay = int(_payload(it, a, r) * pay_scale)
             is_fan = it.kind == "fan" and bool(it.entries)
             fw = 3 + len(it.entries) if is_fan else (1 if it.kind in ("phase", "fan") else 0)
             if ok and ((is_fan and n_fans >= MAX_FANS - 1) or n_gates + 2 >= MAX_GATES - 1
@@ -994,15 +1001,15 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int, direct_io: bool
     for order, gates in encoded_rounds:
         o_lo, o_hi = _pack8(order)
         round_words += [(len(gates) // 3) | ((3 + len(gates)) << 16), o_lo, o_hi] + gates
-    assert len(fan_records) <= MAX_FANS
-
     t_lo, t_hi = _pack8(tile)
     n_fans = len(fan_records)
     directory: List[int] = []
     body: List[int] = []
     pay_len = len(prog._reals) - pay_lo
-    assert pay_len <= MAX_PAYLOAD and sum(len(g) // 3 for _, g in encoded_rounds) <= MAX_GATES
-    assert n_fans + sum(len(rec) for rec in fan_records) <= MAX_FAN_WORDS
+    if (pay_len > MAX_PAYLOAD or sum(len(g) // 3 for _, g in encoded_rounds) > MAX_GATES or n_fans > MAX_FANS
+            or n_fans + sum(len(rec) for rec in fan_records) > MAX_FAN_WORDS):
+        del prog._reals[pay_lo:]                  # nothing else of `prog` has been touched yet
+        raise PassOverflow(f"payload {pay_len}, fans {n_fans}")
     base = 5 + n_fans
     for rec in fan_records:
         directory.append(base + len(body))
@@ -1113,10 +1120,16 @@ def plan(prims: Sequence[Prim], n_qubits: int, cfg: PlanConfig = DEFAULT, n_loca
             prog.add_op(_lib.OP_EXCHANGE, head.t, aux=head.aux, nbytes=16.0 * 2 ** nl)
             prog.n_exchanges += 1
             continue
-        ps, rest = build_pass(remaining, nl, a, r, c, cfg)
-        if not ps.rounds:                                   # cannot happen: the head item always fits
-            raise RuntimeError(f"planner made no progress at {remaining[0]}")
-        encode_pass(prog, ps, nl, r, c, cfg.direct_io, cfg.direct_out)
+        for scale in (0.4, 0.7, 1.0):             # optimistic payload estimate first, the safe bound last
+            ps, rest = build_pass(remaining, nl, a, r, c, cfg, pay_scale=scale)
+            if not ps.rounds:                               # cannot happen: the head item always fits
+                raise RuntimeError(f"planner made no progress at {remaining[0]}")
+            try:
+                encode_pass(prog, ps, nl, r, c, cfg.direct_io, cfg.direct_out)
+                break
+            except PassOverflow:
+                if scale == 1.0:
+                    raise
         remaining = rest
     if sharded:
         prog.n_prims += norm.n_relabelled

@@ -201,16 +201,19 @@ def test_tile_kernel_direct_first_and_last_round(n):
     from qaqarot_b200.planner import PlanConfig
     from qaqarot_b200 import workloads as W
     rng = np.random.default_rng(400 + n)
+    seen = 0
     for circ in (W.qft(n), W.random_layers(n, 6), C.build(Circuit, {"n": n, "ops": C.random_ops(rng, n, 150, True)})):
         be = B200Backend(plan_config=PlanConfig(a=min(n, 12), direct_io=True))
         try:
             got = circ.run(backend=be)
             words = be._compiled.prefix._words
-            flagged = [((words[o[5]] >> 40) & 3) for o in be._compiled.prefix._ops if o[0] == 16]
+            for o in be._compiled.prefix._ops:
+                if o[0] == 16:
+                    seen |= (words[o[5]] >> 40) & 3
         finally:
             be.close()
-        assert any(flagged)
         assert maxabs(got, _oracle(circ)) <= TOL
+    assert seen != 0                     # a direct first or last round really ran
 
 
 @pytest.mark.parametrize("n", [11, 13, 17])
