@@ -154,3 +154,103 @@ def test_pass_bytes_accounting():
     prog = P.plan(low.prims, n)
     assert prog.pass_bytes == pytest.approx(prog.n_passes * 32.0 * 2 ** n)
     assert len(prog.op_bytes) == prog.n_passes
+
+
+# ---- 1-qubit unitaries as phase . rotation-by-shears . phase, layer / table records ------------------------------
+def _random_unitary(rng):
+    z = rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2))
+    q, _ = np.linalg.qr(z)
+    return q.reshape(4)
+
+
+def test_split_shears_reproduces_unitaries_to_rounding():
+    rng = np.random.default_rng(5)
+    h = np.array([1, 1, 1, -1], dtype=complex) / np.sqrt(2)
+    mats = [_random_unitary(rng) for _ in range(2000)] + [h, -h, 1j * h]
+    for t in np.linspace(-7, 7, 58):                        # real rotations / reflections, near-diagonal and near-X
+        c, s = np.cos(t), np.sin(t)
+        mats += [np.array([c, -s, s, c], dtype=complex), np.array([c, s, s, -c], dtype=complex)]
+    for t in 10.0 ** rng.uniform(-9, 0, 200):               # tiny off-diagonal entries with arbitrary phases
+        a, b = rng.uniform(0, 6, 2)
+        mats.append(np.array([np.cos(t), -np.exp(1j * a) * np.sin(t), np.exp(1j * b) * np.sin(t),
+                              np.exp(1j * (a + b)) * np.cos(t)]) * np.exp(0.3j))
+    for m in mats:
+        sp = P.split_shears(m)
+        assert sp is not None
+        g, dl, z, x, y, dr = sp
+        assert abs(abs(g) - 1) < 1e-15 and abs(abs(dl) - 1) < 1e-15 and abs(abs(dr) - 1) < 1e-15
+        assert max(abs(z), abs(x), abs(y)) <= 1.0 + 1e-12   # |theta| <= pi/2: well conditioned shears
+        sm = P.shear_matrix(z, x, y)
+        rec = g * np.array([sm[0], sm[1] * dr, dl * sm[2], dl * sm[3] * dr])
+        assert np.max(np.abs(rec - m)) <= 2e-15
+        if np.all(m.imag == 0) and m[0] * m[3] - m[1] * m[2] > 0:
+            assert dl == 1 and dr == 1                        # a real rotation needs no phases at all
+
+
+def test_split_shears_rejects_non_unitary_matrices():
+    assert P.split_shears(np.array([1, 1, 0, 1], dtype=complex)) is None
+    assert P.split_shears(np.array([1, 0.5, 0.5, 1], dtype=complex)) is None
+    assert P.split_shears(np.array([2, 1j, 1j, 2], dtype=complex) / 2) is None
+
+
+def _records(prog):
+    """(target kind, diag kind) of every gate slot of every tile pass."""
+    out = []
+    for op in prog._ops:
+        if op[0] != _lib.OP_TILE:
+            continue
+        w = prog._words[op[5]:op[5] + op[3]]
+        pos = w[3] >> 32
+        for _ in range((w[0] >> 24) & 0xFF):
+            for g in range(w[pos] & 0xFFFF):
+                g0 = w[pos + 3 + 3 * g]
+                out.append((g0 & 0xFF, (g0 >> 16) & 0xFF))
+            pos += w[pos] >> 16
+    return out
+
+
+def test_layered_circuit_becomes_layer_and_table_records():
+    """H / RZ / CX brick layers: every 1-qubit gate runs as shears inside a LAYER record, every CX as H . CZ . H
+    with the CZ in a table or a fan -- no pair swap and no general 2x2 is left (the pass then runs on the kernel
+    built without those stages, csrc/tile.cu k_tile<..., FULL = false>)."""
+    n = 16
+    low = lower(W.random_layers(n, 6).ops, n)
+    prog = P.plan(low.prims, n)
+    recs = _records(prog)
+    kinds = {tk for tk, _ in recs}
+    assert P.T_LAYER in kinds and not kinds & {P.T_MATC, P.T_MATR, P.T_X}
+    assert any(dk == P.D_TAB for _, dk in recs)
+    n_1q = sum(1 for p in low.prims if p.kind in ("mat", "diag") and not p.controls)
+    assert sum(1 for tk, _ in recs if tk == P.T_LAYER) < n_1q // 2        # several gates per record
+    base = P.plan(low.prims, n, P.PlanConfig(shears=False))
+    assert {tk for tk, _ in _records(base)} & {P.T_MATC, P.T_X}            # the general path is still there
+    ref = O.OracleBackend().run(W.random_layers(n, 6).ops, n)
+    for cfg in (P.PlanConfig(), P.PlanConfig(shears=False)):
+        assert maxabs(W.random_layers(n, 6).run(backend=interp_backend(cfg)), ref) <= TOL
+
+
+def test_cx_chain_through_hadamard_rewrite():
+    """GHZ ladder + rotations around the CX gates: the H . CZ . H rewrite keeps parity."""
+    n = 10
+    c = Circuit(n).h[0]
+    for q in range(n - 1):
+        c.ry(0.3 + q)[q].cx[q, q + 1].rx(0.2 * q)[q + 1]
+    c.cx[n - 1, 0].cx[0, n - 1]
+    ref = O.OracleBackend().run(c.ops, n)
+    for cfg in SMALL + [P.PlanConfig(a=9)]:
+        assert maxabs(c.run(backend=interp_backend(cfg)), ref) <= TOL
+
+
+def test_pass_overflow_falls_back_to_the_safe_payload_bound(monkeypatch):
+    """The optimistic payload estimate may overshoot the kernel's table: the pass is rebuilt, not truncated."""
+    n = 14
+    circ = W.random_layers(n, 10)
+    low = lower(circ.ops, n)
+    monkeypatch.setattr(P, "MAX_PAYLOAD", 400)
+    prog = P.plan(low.prims, n, P.PlanConfig(a=10))
+    for op in prog._ops:
+        if op[0] == _lib.OP_TILE:
+            assert (prog._words[op[5] + 4] >> 32) <= 400
+    st = OracleState(n, 0)
+    st.apply(prog)
+    assert maxabs(st.download(), O.OracleBackend().run(circ.ops, n)) <= TOL
