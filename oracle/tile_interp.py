@@ -77,7 +77,7 @@ def run_tile_pass(psi: np.ndarray, n: int, words: np.ndarray, reals: np.ndarray,
             cond = ((fixed & fm) == fm) & ((local & lm) == lm)
             if tk == T_LAYER:
                 # up to one gate per register bit (reg mask says which), each as three shears; payload 4 x (z, x, y, 0)
-                assert int(fm) == 0 and int(lm) == 0 and 0 < int(rm) < (1 << r)
+                assert int(fm) == 0 and int(lm) == 0 and 0 < (int(rm) & 15) < (1 << r)
                 assert dk in (D_NONE, D_FANT, D_FAN, D_W, D_FIX, D_TAB)
                 pay = cplx(roff_t, 8)
                 for k in range(r):
@@ -128,8 +128,17 @@ def run_tile_pass(psi: np.ndarray, n: int, words: np.ndarray, reals: np.ndarray,
                     psi[keep] *= fan_fixed[fid][keep]
             elif dk == D_TAB:
                 assert int(fm) == 0 and int(lm) == 0, "a table applies to every amplitude"
-                tab = cplx(roff_d, 1 << r)
-                psi *= tab[rho.astype(np.int64)]
+                # one table per combination of (up to) three index bits outside the tile: reg mask bits 4..9 and
+                # 10..15, fan byte (63 = none)
+                ps = [(int(rm) >> 4) & 63, (int(rm) >> 10) & 63, fid]
+                assert all(p == 63 or (p < n + 32 and p not in tile) for p in ps)
+                assert ps == sorted(ps, key=lambda p: p == 63), "used selector bits come first"
+                n_var = 1 << sum(1 for p in ps if p != 63)
+                tab = cplx(roff_d, n_var << r)
+                var = np.zeros_like(fixed)
+                for i, p in enumerate(ps):
+                    var |= ((fixed >> np.uint64(p)) & np.uint64(1)) << np.uint64(i)
+                psi *= tab[(var.astype(np.int64) << r) | rho.astype(np.int64)]
             elif dk == D_PHASE:
                 assert tk == T_NONE
                 keep = cond & ((rho & rm) == rm)

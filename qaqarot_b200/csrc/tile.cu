@@ -42,7 +42,10 @@
 //                  3 = phase  amp *= reals[offset] where rho satisfies reg_mask (never fused with a target stage)
 //                  4 = fan without entries: amp *= reals[offset] on register bit j (a 1-qubit phase, no fan record)
 //                  5 = fan whose entries all lie outside the tile: amp *= fix[fan], no tables
-//                  6 = table: amp[rho] *= reals[offset + rho] (2^R complex), any diagonal on the register bits
+//                  6 = table: amp[rho] *= table[variant][rho] (2^R complex each), any diagonal on the register bits;
+//                      variant = bit p1 | bit p2 << 1 | bit p3 << 2 of the tile's fixed index bits, p1 = reg_mask >> 4
+//                      & 63, p2 = reg_mask >> 10 & 63, p3 = fan byte (63: none) -- fans whose entries lie outside
+//                      the tile ride along
 //     A 2x2 followed by a fan on the same register bit (the H + controlled-phase ladder of a QFT) is one record.
 #include "common.cuh"
 
@@ -556,7 +559,11 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
           if (key1 == kKeyLayer) layer_apply<R>(v, pay_t, rm);       // (rm: which register bits carry a gate)
           else if (FULL && key1 != 0u) run_target<R>(v, key1, rm, pay_t);
           if (key2 == kKeyTab) {
-            tab_apply<R>(v, reinterpret_cast<const double2*>(pay_d));
+            // one table per combination of (up to) three index bits outside the tile (63 = none): CTA-uniform per tile
+            const uint32_t var = (uint32_t)((fixedidx >> ((rm >> 4) & 63u)) & 1ull) |
+                                 ((uint32_t)((fixedidx >> ((rm >> 10) & 63u)) & 1ull) << 1) |
+                                 ((uint32_t)((fixedidx >> ((q.x >> 16) & 63u)) & 1ull) << 2);
+            tab_apply<R>(v, reinterpret_cast<const double2*>(pay_d) + (var << R));
           } else if (key2 != 0u) {
             const uint32_t dk = key2 & 7u;
             c128 wt = make_double2(1.0, 0.0);

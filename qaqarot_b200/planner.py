@@ -659,6 +659,10 @@ def build_pass(remaining: List[Item], n: int, a: int, r: int, c: int, cfg: PlanC
         picked: List[int] = []
         skipped_nd: set = set()
         skipped_dg: set = set()
+        nd_left: Dict[int, int] = {}               # wire -> non-diagonal gates on it still to be scheduled
+        for idx in range(limit):
+            if not done[idx] and remaining[idx].kind in ("mat", "x"):
+                nd_left[remaining[idx].t] = nd_left.get(remaining[idx].t, 0) + 1
         for idx in range(limit):
             if done[idx]:
                 continue
@@ -670,7 +674,10 @@ def build_pass(remaining: List[Item], n: int, a: int, r: int, c: int, cfg: PlanC
             if ok and ((is_fan and n_fans >= MAX_FANS - 1) or n_gates + 2 >= MAX_GATES - 1
                        or payload + pay > MAX_PAYLOAD - 64 or fan_words + fw > MAX_FAN_WORDS - 8):
                 ok = False
-            if ok and it.nd:
+            # a 1-qubit phase in front of a gate on the same wire (the `dr` of split_shears) waits for the round in
+            # which that wire is a register bit: there it is a table entry, anywhere else a record of its own
+            wants_reg = bool(it.nd) or (it.kind == "fan" and not it.entries and nd_left.get(it.t, 0) > 0)
+            if ok and wants_reg:
                 t = it.t
                 new_t = t not in tile
                 new_r = t not in reg
@@ -683,6 +690,8 @@ def build_pass(remaining: List[Item], n: int, a: int, r: int, c: int, cfg: PlanC
                         reg.append(t)
             if ok:
                 picked.append(idx)
+                if it.kind in ("mat", "x"):
+                    nd_left[it.t] -= 1
                 cost += _cost(it)
                 n_fans += is_fan
                 n_gates += 2 if it.kind == "fan" else 1
@@ -748,19 +757,24 @@ def _pack8(vals: Sequence[int]) -> Tuple[int, int]:
 
 class _Group:
     """One LAYER / TAB record being assembled by encode_pass: up to one shear gate per register bit, then one
-    factor per register amplitude (any diagonal on the register bits), or instead of it one fan (`diag`).
-    Items joining the group after other records were emitted are hoisted in front of those, hence the `blocked`
-    sets: register bits on which a shear (`blocked_sh`) or a diagonal (`blocked_dg`) may no longer join."""
+    factor per register amplitude (any diagonal on the register bits), or instead of it one fan (`diag`);
+    `after` holds the records of their own that must run behind it (general 2x2, pair swaps, fans with thread or
+    fixed-bit entries).  encode_pass places every item of a round in the EARLIEST group the commutation rule
+    allows (a shear on register bit k strictly after everything that touches k, a diagonal no earlier than the
+    last non-diagonal gate on its bits), so gates of one circuit layer share a record even when the program
+    lists them interleaved with the phases between them."""
 
     def __init__(self, r: int):
         self.r = r
         self.sh: Dict[int, Tuple[float, float, float]] = {}     # register bit -> (z, x, y)
         self.tab = np.ones(1 << r, dtype=complex)
         self.has_tab = False
-        self.diag: Optional[dict] = None
-        self.clean = True                                        # no foreign record since the group opened
-        self.blocked_sh: set = set()
-        self.blocked_dg: set = set()
+        self.diag: Optional[dict] = None                         # a fan fused as the record's diag stage
+        self.after: List[dict] = []
+        # fans on a register bit whose entries all sit on index bits OUTSIDE the tile are constant per tile: for up
+        # to three such bits the table is stored once per combination and the kernel picks the variant per tile
+        self.fixed_bits: List[int] = []
+        self.fix_fans: List[Tuple[int, Dict[int, complex]]] = []
 
     def mul_phase(self, regs, w: complex) -> None:
         mask = sum(1 << k for k in regs)
@@ -768,6 +782,15 @@ class _Group:
             if rho & mask == mask:
                 self.tab[rho] *= w
         self.has_tab = True
+
+    def take_fixed(self, kt: int, entries: Dict[int, complex]) -> bool:
+        bits = self.fixed_bits + [q for q in entries if q not in self.fixed_bits]
+        if len(bits) > 3 or self.diag is not None:
+            return False
+        self.fixed_bits = bits
+        self.fix_fans.append((kt, dict(entries)))
+        self.has_tab = True
+        return True
 
     def mul_fan(self, kt: int, w0: complex, entries: Dict[int, complex]) -> None:
         for rho in range(1 << self.r):
@@ -781,15 +804,30 @@ class _Group:
 
     def words_kw(self, prog: Program, r: int) -> Optional[dict]:
         kw: dict = {}
+        p = self.fixed_bits + [63] * (3 - len(self.fixed_bits))      # 63: no such bit (reads as 0 in every tile)
+        sel = (p[0] << 4) | (p[1] << 10)
         if self.sh:
             pay: List[complex] = []
             for k in range(4):
                 z, x, y = self.sh.get(k, (0.0, 0.0, 0.0))
                 pay += [complex(z, x), complex(y, 0.0)]
-            kw = dict(tk=T_LAYER, rm=sum(1 << k for k in self.sh), roff_t=prog.add_reals(pay))
+            kw = dict(tk=T_LAYER, rm=sum(1 << k for k in self.sh) | sel, roff_t=prog.add_reals(pay))
         if self.has_tab:
             assert self.diag is None
-            kw.update(dk=D_TAB, roff_d=prog.add_reals(list(self.tab)))
+            tabs: List[complex] = []
+            for var in range(1 << len(self.fixed_bits)):
+                t = self.tab.copy()
+                for kt, entries in self.fix_fans:
+                    f = 1.0 + 0j
+                    for q, w in entries.items():
+                        if (var >> self.fixed_bits.index(q)) & 1:
+                            f *= w
+                    for rho in range(1 << self.r):
+                        if (rho >> kt) & 1:
+                            t[rho] *= f
+                tabs += list(t)
+            kw.update(dk=D_TAB, roff_d=prog.add_reals(tabs), fid=p[2])
+            kw.setdefault("rm", sel)
         elif self.diag is not None:
             kw.update(j=self.diag["j"], dk=self.diag["dk"], fid=self.diag["fid"], roff_d=self.diag["roff_d"])
         return kw or None
@@ -874,15 +912,11 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int, direct_io: bool
     encoded_rounds: List[Tuple[List[int], List[int]]] = []
     for rd in ps.rounds:
         order = _thread_order(tile, rd.reg)
-        out: List[object] = []                    # gate_words keyword dicts and _Group objects, in execution order
-        pending_t: Optional[dict] = None          # target stage waiting for a fan on the same register bit
-        grp: Optional[_Group] = None              # open layer / table record (see _Group)
-
-        def flush_t():
-            nonlocal pending_t
-            if pending_t is not None:
-                out.append(pending_t)
-                pending_t = None
+        slots: List[_Group] = [_Group(r)]
+        last_any = [-1] * r          # per register bit: last slot holding anything that touches it
+        last_nd = [-1] * r           # ... last slot holding (or followed by) a non-diagonal gate on it
+        diag_min = [0] * r           # ... first slot whose table / `after` list may take a diagonal on it
+        open_nd: Dict[int, dict] = {}     # register bit -> general 2x2 record still open for a fan on the same bit
 
         def reg_index(q) -> Optional[int]:
             li = loc.get(q)
@@ -891,108 +925,142 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int, direct_io: bool
             k = order.index(li)
             return k if k < r else None
 
-        def foreign(kw: dict, nd_bits, dg_bits):
-            """A record of its own after the open group: later gates may join the group only if they commute with it."""
-            out.append(kw)
-            if grp is not None:
-                grp.clean = False
-                for q in nd_bits:
-                    k = reg_index(q)
-                    if k is not None:
-                        grp.blocked_sh.add(k)
-                        grp.blocked_dg.add(k)
-                for q in dg_bits:
-                    k = reg_index(q)
-                    if k is not None:
-                        grp.blocked_sh.add(k)
+        def slot(i: int) -> _Group:
+            while len(slots) <= i:
+                slots.append(_Group(r))
+            return slots[i]
+
+        def touch(regs, i: int):
+            for k in regs:
+                last_any[k] = max(last_any[k], i)
+                open_nd.pop(k, None)
+
+        def table_slot(regs) -> _Group:
+            """Earliest group whose table may take a diagonal on register bits `regs`."""
+            i = max([diag_min[k] for k in regs] + [0])
+            while slot(i).diag is not None:
+                i += 1
+            touch(regs, i)
+            return slots[i]
+
+        def attach(kw: dict, regs_dg, i: int):
+            """A diagonal record of its own, behind group i."""
+            slot(i).after.append(kw)
+            touch(regs_dg, i)
+
+        def emit_fan(t: int, w0: complex, entries: Dict[int, complex]):
+            bits = (t,) + tuple(entries)
+            if not any(q in loc for q in bits):                       # constant over a tile
+                scalars.append((1 << t, w0))
+                scalars.extend(((1 << t) | (1 << q), w) for q, w in entries.items())
+                return
+            regs = [reg_index(q) for q in bits]
+            kt = regs[0]
+            if all(k is not None for k in regs):
+                # purely on register bits: one factor per register amplitude, shared by every thread
+                table_slot(regs).mul_fan(kt, w0, {reg_index(q): w for q, w in entries.items()})
+                return
+            if kt is None and any(k is not None for k in regs[1:]):
+                # target outside the registers, some entries inside: a 2-qubit phase is symmetric, so each such entry
+                # becomes a fan on ITS register bit with the old target as its only entry
+                rest = {}
+                for q, w in entries.items():
+                    if reg_index(q) is not None:
+                        emit_fan(q, 1.0 + 0j, {t: w})
+                    else:
+                        rest[q] = w
+                if rest or w0 != 1.0:
+                    emit_fan(t, w0, rest)
+                return
+            touched = [k for k in regs if k is not None]
+            i = max([diag_min[k] for k in touched] + [0])
+            g = slot(i)
+            nd_kw = open_nd.get(kt) if kt is not None else None
+            if nd_kw is not None and all(last_nd[k] <= last_any[kt] for k in touched):
+                # general 2x2 on a register bit followed by a fan on the same bit: one record, one dispatch
+                fixed = [(1 << q, w) for q, w in entries.items() if q not in loc]
+                lw = {loc[q]: w for q, w in entries.items() if q in loc}
+                f = fan_fields(order, fixed, w0, lw, t)
+                nd_kw.update(dk=f["dk"], fid=f["fid"], roff_d=f["roff_d"])
+                touch(touched, last_any[kt])
+                return
+            has_reg_entries = any(k is not None for k in regs[1:])
+            if (kt is not None and (has_reg_entries or len(g.sh) == 1) and kt in g.sh and not g.has_tab
+                    and g.diag is None and not g.after and last_any[kt] == i):
+                # shears on bit kt followed at once by a fan with register AND other entries (the H + controlled-
+                # phase ladder of a QFT): the fan with its register table is the record's diag stage
+                fixed = [(1 << q, w) for q, w in entries.items() if q not in loc]
+                lw = {loc[q]: w for q, w in entries.items() if q in loc}
+                g.diag = fan_fields(order, fixed, w0, lw, t)
+                touch(touched, i)
+                return
+            if kt is not None and has_reg_entries:
+                # the factors between register bits go into a table, the rest stays a fan
+                reg_part = {reg_index(q): w for q, w in entries.items() if reg_index(q) is not None}
+                table_slot([kt] + list(reg_part)).mul_fan(kt, 1.0 + 0j, reg_part)
+                entries = {q: w for q, w in entries.items() if reg_index(q) is None}
+                touched = [kt]
+                if not entries and w0 == 1.0:
+                    return
+            if kt is not None and entries and all(q not in loc for q in entries):
+                # constant per tile: a table variant instead of a record of its own, if the group has room
+                i = diag_min[kt]
+                if slot(i).take_fixed(kt, entries):
+                    slots[i].mul_fan(kt, w0, {})
+                    touch([kt], i)
+                    return
+            fixed = [(1 << q, w) for q, w in entries.items() if q not in loc]
+            lw = {loc[q]: w for q, w in entries.items() if q in loc}
+            attach(fan_fields(order, fixed, w0, lw, t), touched, max([diag_min[k] for k in touched] + [0]))
 
         for it in rd.items:
             n_prims += it.n_prims
             if it.kind == "mat" and it.sh is not None:
-                flush_t()
                 k = reg_index(it.t)
                 assert k is not None and not it.ctrls, "non-diagonal target outside the round's register bits"
-                if grp is None or k in grp.blocked_sh:
-                    grp = _Group(r)
-                    out.append(grp)
-                grp.sh[k] = it.sh
-                grp.blocked_sh.add(k)
-                continue
-            if it.kind in ("mat", "x"):
-                flush_t()
-                j = order.index(loc[it.t])
-                assert j < r, "non-diagonal target outside the round's register bits"
+                i = last_any[k] + 1
+                slot(i).sh[k] = it.sh
+                touch([k], i)
+                last_nd[k] = i
+                diag_min[k] = i
+            elif it.kind in ("mat", "x"):
+                k = reg_index(it.t)
+                assert k is not None, "non-diagonal target outside the round's register bits"
                 lm, rm, fm = split_mask(it.ctrls, order)
                 if it.kind == "mat":
                     real = bool(np.all(np.asarray(it.m).imag == 0))
-                    kw = dict(tk=T_MATR if real else T_MATC, j=j, lm=lm, rm=rm, fm=fm, roff_t=prog.add_reals(it.m))
+                    kw = dict(tk=T_MATR if real else T_MATC, j=k, lm=lm, rm=rm, fm=fm, roff_t=prog.add_reals(it.m))
                 else:
-                    kw = dict(tk=T_X, j=j, lm=lm, rm=rm, fm=fm)
-                if grp is not None:
-                    foreign({}, (it.t,), it.ctrls)
-                    out.pop()
-                pending_t = kw
-                continue
-            # ---- diagonal items ------------------------------------------------------------------------------
-            bits = it.bits if it.kind == "phase" else (it.t,) + tuple(it.entries)
-            if not any(q in loc for q in bits):
-                if it.kind == "phase":
-                    scalars.append((sum(1 << q for q in it.bits), it.w))
-                else:
-                    scalars.append((1 << it.t, it.w))
-                    scalars += [((1 << it.t) | (1 << q), w) for q, w in it.entries.items()]
-                continue
-            regs = [reg_index(q) for q in bits]
-            if all(k is not None for k in regs) and pending_t is None:
-                # purely on register bits: one factor per register amplitude, shared by every thread
-                if grp is None or grp.diag is not None or (set(regs) & grp.blocked_dg):
-                    grp = _Group(r)
-                    out.append(grp)
-                if it.kind == "phase":
-                    grp.mul_phase(regs, it.w)
-                else:
-                    grp.mul_fan(regs[0], it.w, {reg_index(q): w for q, w in it.entries.items()})
-                grp.blocked_sh |= set(regs)
-                continue
-            if it.kind == "phase":
-                flush_t()
-                lm, rm, fm = split_mask(it.bits, order)
-                foreign(gate_words_kw(dk=D_PHASE, lm=lm, rm=rm, fm=fm, roff_d=prog.add_reals([it.w])), (), bits)
-                continue
-            kt = reg_index(it.t)
-            can_fuse = (pending_t is None and grp is not None and grp.clean and grp.sh and not grp.has_tab
-                        and grp.diag is None and kt is not None)
-            entries, w0 = dict(it.entries), it.w
-            if (not can_fuse and pending_t is None and grp is not None and grp.diag is None and kt is not None
-                    and kt not in grp.blocked_dg):
-                # the factors between register bits go into the group's table, the rest stays a fan
-                reg_part = {reg_index(q): w for q, w in entries.items() if reg_index(q) is not None}
-                if reg_part and not (set(reg_part) & grp.blocked_dg):
-                    grp.mul_fan(kt, 1.0 + 0j, reg_part)
-                    grp.blocked_sh |= set(reg_part) | {kt}
-                    entries = {q: w for q, w in entries.items() if reg_index(q) is None}
-            fixed = [(1 << q, w) for q, w in entries.items() if q not in loc]
-            lw = {loc[q]: w for q, w in entries.items() if q in loc}
-            f = fan_fields(order, fixed, w0, lw, it.t)
-            if can_fuse:
-                grp.diag = f
-                grp.blocked_sh |= {k for k in regs if k is not None}
-            elif (pending_t is not None and pending_t["j"] == f["j"] and f["j"] < r and pending_t["lm"] == 0
-                    and pending_t["fm"] == 0 and pending_t["rm"] == 0 and pending_t["tk"] != T_X):
-                # 2x2 on a register bit followed by a fan on the same bit: one record, one dispatch
-                pending_t.update(dk=f["dk"], fid=f["fid"], roff_d=f["roff_d"])
-                flush_t()
-                if grp is not None:
-                    foreign({}, (), bits)
-                    out.pop()
+                    kw = dict(tk=T_X, j=k, lm=lm, rm=rm, fm=fm)
+                cregs = [reg_index(q) for q in it.ctrls if reg_index(q) is not None]
+                i = max([last_any[k]] + [last_nd[c] for c in cregs] + [0])
+                slot(i).after.append(kw)
+                touch([k] + cregs, i)
+                last_nd[k] = i
+                diag_min[k] = i + 1
+                if it.kind == "mat" and lm == 0 and rm == 0 and fm == 0:
+                    open_nd[k] = kw
+            elif it.kind == "phase":
+                bits = it.bits
+                if not any(q in loc for q in bits):
+                    scalars.append((sum(1 << q for q in bits), it.w))
+                    continue
+                regs = [reg_index(q) for q in bits]
+                if all(k is not None for k in regs):
+                    table_slot(regs).mul_phase(regs, it.w)
+                    continue
+                lm, rm, fm = split_mask(bits, order)
+                touched = [k for k in regs if k is not None]
+                attach(dict(dk=D_PHASE, lm=lm, rm=rm, fm=fm, roff_d=prog.add_reals([it.w])), touched,
+                       max([diag_min[k] for k in touched] + [0]))
             else:
-                flush_t()
-                foreign(f, (), bits)
-        flush_t()
+                emit_fan(it.t, it.w, dict(it.entries))
         gates: List[int] = []
-        for e in out:
-            kw = e.words_kw(prog, r) if isinstance(e, _Group) else e
+        for g in slots:
+            kw = g.words_kw(prog, r)
             if kw:
+                gates += gate_words(**kw)
+            for kw in g.after:
                 gates += gate_words(**kw)
         encoded_rounds.append((order, gates))
     if scalars:
