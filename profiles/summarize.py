@@ -24,7 +24,7 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "lts__t_sector_hit_rate.pct"]
 scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}
 lines = [f"# ncu --set full: {os.path.basename(rep)}", "",
-         "`ncu --set full --clock-control none --import-source on -k regex:\"k_tile|k_involution\" -s 15 -c 5 "
+         "`ncu --set full --clock-control none --import-source on -k regex:\"k_tile|k_involution\" -s 12 -c 4 "
          "python bench.py --steps 1 --warmup 3 --no-cpu` under gpurun on one B200 (the passes of one timed step of the "
          f"{n}-qubit QFT).  Per-launch times under ncu are cold-cache and serialised; the un-profiled CUDA-event "
          "times are in the bench JSON next to this file.", ""]
