@@ -21,8 +21,9 @@
 //
 // Descriptor (uint64 words, produced by qaqarot_b200/planner.py::encode_pass; `reals` = float64 pool):
 //   D[0] = A | c<<8 | R<<16 | n_rounds<<24 | n_fans<<32 | flags<<40   D[1], D[2] = tile bit positions, 8 bits each
-//          flags: 1 = the first round loads straight from HBM, 2 = the last round stores straight to HBM (its
-//          register bits avoid the c row bits, so a half warp still covers one contiguous 2^c * 16 B row)
+//          flags: 2 = the last round stores straight to HBM (its register bits avoid the c row bits, so a half
+//          warp still covers one contiguous 2^c * 16 B row); 1 = same for the first round's loads: accepted and
+//          ignored (measured neutral; the code was removed to keep the kernel small)
 //   D[3] = fan directory offset | rounds offset << 32      D[4] = first payload real | payload length << 32
 //          (everything the pass reads from `reals` is that one range; each CTA keeps a copy in shared memory)
 //   fan directory: n_fans word offsets; fan record: n_entries | roff<<32, then n_entries masks.
@@ -68,10 +69,6 @@ __host__ __device__ constexpr uint32_t swz_c(uint32_t l) {
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
-}
-// Pull `bytes` (multiple of 16) starting at a 16-byte aligned global address into L2 (no SM-side destination).
-__device__ __forceinline__ void prefetch_l2_bulk(const void* gmem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem_src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
@@ -127,14 +124,15 @@ __device__ __forceinline__ void pair_mat_r(c128& a0, c128& a1, double m00, doubl
       : "+d"(a0.x), "+d"(a0.y), "+d"(a1.x), "+d"(a1.y)
       : "d"(m00), "d"(m01), "d"(m10), "d"(m11));
 }
-// a <- a * f   (nfy = -f.y)
+// a <- a * f   (nfy = -f.y).  Both products of a.y first, then a.y and a.x are overwritten in that order: four FP64
+// instructions and no copy (the first version computed a.x into a temporary and moved it back: 2 more issue slots per
+// amplitude, in records that are ~75 % issue-bound).
 __device__ __forceinline__ void amp_mul(c128& a, double fx, double fy, double nfy) {
   asm("{\n\t.reg .f64 t0, t1;\n\t"
-      "mul.f64 t0, %0, %2;\n\t"
-      "mul.f64 t1, %1, %2;\n\t"
-      "fma.rn.f64 t0, %1, %4, t0;\n\t"
-      "fma.rn.f64 %1, %0, %3, t1;\n\t"
-      "mov.f64 %0, t0;\n\t}"
+      "mul.f64 t0, %1, %4;\n\t"          // a.y * -f.y
+      "mul.f64 t1, %1, %2;\n\t"          // a.y *  f.x
+      "fma.rn.f64 %1, %0, %3, t1;\n\t"   // a.y = a.x f.y + a.y f.x
+      "fma.rn.f64 %0, %0, %2, t0;\n\t}"  // a.x = a.x f.x - a.y f.y
       : "+d"(a.x), "+d"(a.y)
       : "d"(fx), "d"(fy), "d"(nfy));
 }
@@ -309,8 +307,8 @@ struct TileSmem {
   uint32_t thr[kMaxRounds][1 << (A - R)];   // per round, per thread: local index bits | swizzled byte offset / 16 << 16
   uint32_t round_off[kMaxRounds];
   // direct global <-> register access of the first / last round (when its register bits avoid the row bits):
-  uint64_t gthr[2][1 << (A - R)];  // per thread: where its thread bits sit in the index space
-  uint64_t ghb[2][4];              // per register bit: its index bit as a mask
+  uint64_t gthr[1 << (A - R)];     // per thread: where its thread bits sit in the index space
+  uint64_t ghb[4];                 // per register bit: its index bit as a mask
 };
 
 // ---- the kernel ------------------------------------------------------------------------------------------------
@@ -333,12 +331,13 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
   const uint64_t h0 = desc[0], tb_lo = desc[1], tb_hi = desc[2];
   const int n_rounds = (int)((h0 >> 24) & 0xFF), n_fans = (int)((h0 >> 32) & 0xFF);
   const uint32_t dir_off = (uint32_t)(desc[3] & 0xFFFFFFFFu), rounds_off = (uint32_t)(desc[3] >> 32);
-  const int c_bits = (int)((h0 >> 8) & 0xFF);
   const uint32_t pay_lo = (uint32_t)(desc[4] & 0xFFFFFFFFu), pay_len = (uint32_t)(desc[4] >> 32);
   // flags bit 1: the state is a basis vector that nobody has written yet -- every tile is all zeros except
   // tile `init_tile`, whose local index `init_local` holds 1 (B200_OP_INIT folded into this pass)
   const bool init = (flags & 2u) != 0;
-  const bool direct_in = ((h0 >> 40) & 1) != 0 && !init, direct_out = ((h0 >> 41) & 1) != 0;
+  // (flag 1, "first round loads straight from HBM", is accepted and ignored: measured neutral, and its code cost
+  // every record ~0.01 ms -- see the note on kernel size at k_tile)
+  const bool direct_out = ((h0 >> 41) & 1) != 0;
 
   // ---- one-time setup ----------------------------------------------------------------------------------------
   if (tid == 0) {
@@ -366,16 +365,11 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
     uint32_t lt = 0;
     for (int b = 0; b < NTB; ++b) lt |= ((tid >> b) & 1u) << byte_of(o_lo, o_hi, R + b);
     S.thr[rd][tid] = lt | (swz(lt) << 16);
-    if (rd == 0 || rd == n_rounds - 1) {
+    if (rd == n_rounds - 1) {      // the last round may store straight to HBM (flag 2)
       uint64_t go = 0;
       for (int b = 0; b < A; ++b) go |= (uint64_t)((lt >> b) & 1u) << byte_of(tb_lo, tb_hi, b);
-      if (rd == 0) S.gthr[0][tid] = go;
-      if (rd == n_rounds - 1) S.gthr[1][tid] = go;
-      if (tid < R) {
-        const uint64_t hbm = 1ull << byte_of(tb_lo, tb_hi, byte_of(o_lo, o_hi, tid));
-        if (rd == 0) S.ghb[0][tid] = hbm;
-        if (rd == n_rounds - 1) S.ghb[1][tid] = hbm;
-      }
+      S.gthr[tid] = go;
+      if (tid < R) S.ghb[tid] = 1ull << byte_of(tb_lo, tb_hi, byte_of(o_lo, o_hi, tid));
     }
     if (tid < R) S.rh[rd].srb[tid] = (uint16_t)swz(1u << byte_of(o_lo, o_hi, tid));
     const int ng = S.rh[rd].n_gates, first = S.rh[rd].first;
@@ -398,10 +392,6 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
 #pragma unroll
   for (int b = 0; b < NTB; ++b) off_t |= (uint64_t)((tid >> b) & 1u) << byte_of(tb_lo, tb_hi, b);
   const uint32_t sw_t = swz(tid) << 4;              // byte offset of this thread's slot for i = 0
-  // rows of 2^c contiguous amplitudes; this thread prefetches row(s) tid, tid + NT, ... of its *next* tile into L2
-  const uint32_t n_rows = 1u << (A - c_bits), row_bytes = 16u << c_bits;
-  uint64_t pref_off = 0;
-  for (int b = c_bits; b < A; ++b) pref_off |= (uint64_t)((tid >> (b - c_bits)) & 1u) << byte_of(tb_lo, tb_hi, b);
   __syncthreads();
 
   auto spread_tile = [&](uint64_t t) -> uint64_t {
@@ -422,7 +412,7 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
   };
   // flags bit 2 (with a direct last round): the next tile's cp.async is issued as soon as every warp has taken
   // the last round's amplitudes out of shared memory, so its HBM latency hides under that round's gates
-  const bool overlap = (flags & 4u) != 0 && direct_out && !direct_in && !init;
+  const bool overlap = (flags & 4u) != 0 && direct_out && !init;
   bool loaded = false;
   uint32_t parity = 0;
   for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, parity ^= 1u) {
@@ -431,36 +421,8 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
     const uint64_t fixedidx = base | index_offset;
     const uint32_t fx_lo = (uint32_t)fixedidx, fx_hi = (uint32_t)(fixedidx >> 32);
     c128* __restrict__ g = amp + base + off_t;
-    if ((flags & 1u) && tile + gridDim.x < n_tiles) {
-      const c128* nb = amp + spread_tile(tile + gridDim.x);
-      if (n_rows == (uint32_t)NT) {
-        prefetch_l2_bulk(nb + pref_off, row_bytes);
-      } else {
-        for (uint32_t row = tid; row < n_rows; row += NT) {
-          uint64_t roff = 0;
-          for (int b = c_bits; b < A; ++b) roff |= (uint64_t)((row >> (b - c_bits)) & 1u) << byte_of(tb_lo, tb_hi, b);
-          prefetch_l2_bulk(nb + roff, row_bytes);
-        }
-      }
-    }
-
     c128 v[PER];
-    if (direct_in) {
-      // round 0 keeps no row bit in registers: its 16 amplitudes per thread come straight from HBM, a half
-      // warp per 256-byte row, no shared-memory staging and no barrier before the first gate
-      const c128* __restrict__ gi = amp + base + S.gthr[0][tid];
-      uint64_t hb[R];
-#pragma unroll
-      for (int k = 0; k < R; ++k) hb[k] = S.ghb[0][k];
-#pragma unroll
-      for (int rho = 0; rho < PER; ++rho) {
-        uint64_t off = 0;
-#pragma unroll
-        for (int k = 0; k < R; ++k)
-          if ((rho >> k) & 1) off |= hb[k];
-        v[rho] = __ldcg(gi + off);
-      }
-    } else if (init) {
+    if (init) {
 #pragma unroll
       for (int i = 0; i < PER; ++i)
         *reinterpret_cast<c128*>(reinterpret_cast<unsigned char*>(sm) + (sw_t ^ (swz_c((uint32_t)i * NT) << 4))) =
@@ -501,7 +463,7 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
       if (lane == 0) fixp[f] = cmul(p, w[0]);
     }
     tick(0);                      // fan products
-    if (!direct_in && !init) cp_async_wait_all();
+    if (!init) cp_async_wait_all();
     __syncthreads();              // tile (or fan products) ready; also: every warp has left the previous tile
     if (init && tile == init_tile) {
       if (tid == 0) sm[swz(init_local)] = make_double2(1.0, 0.0);
@@ -518,7 +480,7 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
       unsigned char* const smb = reinterpret_cast<unsigned char*>(sm);
 
       // Gray-code walk over the 2^R register amplitudes: one XOR per shared-memory address
-      if (!(direct_in && rd == 0)) {
+      {
         uint32_t s = stb;
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
@@ -583,10 +545,10 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
 
       tick(3);                    // round: gates
       if (direct_out && rd == n_rounds - 1) {
-        c128* __restrict__ go = amp + base + S.gthr[1][tid];
+        c128* __restrict__ go = amp + base + S.gthr[tid];
         uint64_t hb[R];
 #pragma unroll
-        for (int k = 0; k < R; ++k) hb[k] = S.ghb[1][k];
+        for (int k = 0; k < R; ++k) hb[k] = S.ghb[k];
 #pragma unroll
         for (int rho = 0; rho < PER; ++rho) {
           uint64_t off = 0;
@@ -625,7 +587,7 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
     tick(6);                      // stream the tile back
     // the next tile's cp.async must not overwrite slots still being read (a direct first round writes shared
     // memory only after the barrier at the head of the next tile)
-    if (!(direct_in && direct_out) && !overlap) __syncthreads();
+    if (!overlap) __syncthreads();
     tick(7);                      // end-of-tile barrier
   }
 }
@@ -642,8 +604,8 @@ static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals,
     configured[st->device & 63] = true;
   }
   const uint64_t n_tiles = st->dim >> A;
-  // persistent: exactly the resident CTAs, each walking tiles blockIdx, blockIdx + grid, ... so that it can
-  // prefetch its next tile into L2 while it works on the current one
+  // persistent: exactly the resident CTAs, each walking tiles blockIdx, blockIdx + grid, ... (it requests its
+  // next tile while the last round of the current one still runs)
   static const int ctas_env = getenv("B200_TILE_CTAS_PER_SM") ? atoi(getenv("B200_TILE_CTAS_PER_SM")) : 0;   // experiment
   const uint64_t cap = (uint64_t)kSMs * (ctas_env > 0 && ctas_env < MINB ? ctas_env : MINB);
   const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
@@ -653,9 +615,7 @@ static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals,
     B200_CUDA(cudaMalloc(&d_cyc, 9 * sizeof(unsigned long long)));
     B200_CUDA(cudaMemsetAsync(d_cyc, 0, 9 * sizeof(unsigned long long), st->stream));
   }
-  // L2 prefetch of the next tile: measured no gain (the loads of a tile already overlap the other CTA's gates)
-  // and ~2000 cycles per tile spent issuing 256 bulk prefetches; off unless B200_TILE_PREFETCH is set
-  static const uint32_t flags = (getenv("B200_TILE_PREFETCH") ? 1u : 0u) | (getenv("B200_TILE_NO_OVERLAP") ? 0u : 4u);
+  static const uint32_t flags = getenv("B200_TILE_NO_OVERLAP") ? 0u : 4u;     // (bit 0 was the L2 prefetch: removed)
   if (timing)
     k_tile<A, R, MINB, true, FULL><<<grid, NT, smem, st->stream>>>(st->amp, n_tiles, st->index_offset, d_desc, d_reals, d_cyc,
                                                              flags | (init ? 2u : 0u), init_tile, init_local);
