@@ -128,17 +128,22 @@ def run_tile_pass(psi: np.ndarray, n: int, words: np.ndarray, reals: np.ndarray,
                     psi[keep] *= fan_fixed[fid][keep]
             elif dk == D_TAB:
                 assert int(fm) == 0 and int(lm) == 0, "a table applies to every amplitude"
-                # one table per combination of (up to) three index bits outside the tile: reg mask bits 4..9 and
-                # 10..15, fan byte (63 = none)
+                # table[rho][variant]; variant = up to three selector bits: reg mask bits 4..9 and 10..15, fan byte.
+                # A selector < 48 is an index bit outside the tile, 48 + l the tile-local thread bit l, 63 none.
                 ps = [(int(rm) >> 4) & 63, (int(rm) >> 10) & 63, fid]
-                assert all(p == 63 or (p < n + 32 and p not in tile) for p in ps)
                 assert ps == sorted(ps, key=lambda p: p == 63), "used selector bits come first"
-                n_var = 1 << sum(1 for p in ps if p != 63)
-                tab = cplx(roff_d, n_var << r)
+                m = sum(1 for p in ps if p != 63)
                 var = np.zeros_like(fixed)
-                for i, p in enumerate(ps):
-                    var |= ((fixed >> np.uint64(p)) & np.uint64(1)) << np.uint64(i)
-                psi *= tab[(var.astype(np.int64) << r) | rho.astype(np.int64)]
+                for i, p in enumerate(ps[:m]):
+                    if p < 48:
+                        assert p not in tile and p < n + 32
+                        bit = (fixed >> np.uint64(p)) & np.uint64(1)
+                    else:
+                        assert p - 48 in order[r:], "a selector inside the tile must be a thread bit of the round"
+                        bit = (local >> np.uint64(p - 48)) & np.uint64(1)
+                    var |= bit << np.uint64(i)
+                tab = cplx(roff_d, (1 << r) << m)
+                psi *= tab[(rho.astype(np.int64) << m) | var.astype(np.int64)]
             elif dk == D_PHASE:
                 assert tk == T_NONE
                 keep = cond & ((rho & rm) == rm)

@@ -43,10 +43,11 @@
 //                  3 = phase  amp *= reals[offset] where rho satisfies reg_mask (never fused with a target stage)
 //                  4 = fan without entries: amp *= reals[offset] on register bit j (a 1-qubit phase, no fan record)
 //                  5 = fan whose entries all lie outside the tile: amp *= fix[fan], no tables
-//                  6 = table: amp[rho] *= table[variant][rho] (2^R complex each), any diagonal on the register bits;
-//                      variant = bit p1 | bit p2 << 1 | bit p3 << 2 of the tile's fixed index bits, p1 = reg_mask >> 4
-//                      & 63, p2 = reg_mask >> 10 & 63, p3 = fan byte (63: none) -- fans whose entries lie outside
-//                      the tile ride along
+//                  6 = table: amp[rho] *= table[rho][variant] (2^R x 2^m complex), any diagonal on the register bits;
+//                      variant = selector bits p1 | p2 << 1 | p3 << 2 with p1 = reg_mask >> 4 & 63, p2 = reg_mask >> 10
+//                      & 63, p3 = fan byte; a selector < 48 is an index bit outside the tile, 48 + l the tile-local
+//                      thread bit l, 63 none (m = selectors in use, packed first) -- fans and phases whose other
+//                      qubits are not register bits ride along as variants
 //     A 2x2 followed by a fan on the same register bit (the H + controlled-phase ladder of a QFT) is one record.
 #include "common.cuh"
 
@@ -228,11 +229,13 @@ __device__ __forceinline__ void layer_apply(c128 (&v)[1 << R], const double* __r
     }
   }
 }
+// amp[rho] *= tab[rho * stride]: the table of this thread's variant (entries of one rho for all variants are adjacent,
+// so the threads of a warp that picked different variants read different banks)
 template <int R>
-__device__ __forceinline__ void tab_apply(c128 (&v)[1 << R], const double2* __restrict__ tab) {
+__device__ __forceinline__ void tab_apply(c128 (&v)[1 << R], const double2* __restrict__ tab, uint32_t stride) {
 #pragma unroll
-  for (int rho = 1; rho < (1 << R); ++rho) {
-    const double2 f = tab[rho];
+  for (int rho = 0; rho < (1 << R); ++rho) {
+    const double2 f = tab[rho * stride];
     amp_mul(v[rho], f.x, f.y, -f.y);
   }
 }
@@ -521,11 +524,14 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
           if (key1 == kKeyLayer) layer_apply<R>(v, pay_t, rm);       // (rm: which register bits carry a gate)
           else if (FULL && key1 != 0u) run_target<R>(v, key1, rm, pay_t);
           if (key2 == kKeyTab) {
-            // one table per combination of (up to) three index bits outside the tile (63 = none): CTA-uniform per tile
-            const uint32_t var = (uint32_t)((fixedidx >> ((rm >> 4) & 63u)) & 1ull) |
-                                 ((uint32_t)((fixedidx >> ((rm >> 10) & 63u)) & 1ull) << 1) |
-                                 ((uint32_t)((fixedidx >> ((q.x >> 16) & 63u)) & 1ull) << 2);
-            tab_apply<R>(v, reinterpret_cast<const double2*>(pay_d) + (var << R));
+            // one table per combination of (up to) three selector bits: index bits outside the tile (CTA-uniform per
+            // tile) or thread bits of the tile (48 + local position); 63 = none, which reads as 0
+            const uint32_t p1 = (rm >> 4) & 63u, p2 = (rm >> 10) & 63u, p3 = (q.x >> 16) & 63u;
+            const uint64_t sel = fixedidx | ((uint64_t)lt << 48);
+            const uint32_t var = (uint32_t)((sel >> p1) & 1ull) | ((uint32_t)((sel >> p2) & 1ull) << 1) |
+                                 ((uint32_t)((sel >> p3) & 1ull) << 2);
+            const uint32_t m = (p1 != 63u) + (p2 != 63u) + (p3 != 63u);
+            tab_apply<R>(v, reinterpret_cast<const double2*>(pay_d) + var, 1u << m);
           } else if (key2 != 0u) {
             const uint32_t dk = key2 & 7u;
             c128 wt = make_double2(1.0, 0.0);

@@ -771,10 +771,11 @@ class _Group:
         self.has_tab = False
         self.diag: Optional[dict] = None                         # a fan fused as the record's diag stage
         self.after: List[dict] = []
-        # fans on a register bit whose entries all sit on index bits OUTSIDE the tile are constant per tile: for up
-        # to three such bits the table is stored once per combination and the kernel picks the variant per tile
-        self.fixed_bits: List[int] = []
-        self.fix_fans: List[Tuple[int, Dict[int, complex]]] = []
+        # a fan (or phase) whose qubits other than its register-bit target are NOT register bits depends, per thread
+        # and per tile, on those bits only: for up to three such *selector* bits (index bits outside the tile,
+        # thread bits of the tile as 48 + local position) the table is stored once per combination
+        self.sel_bits: List[int] = []
+        self.sel_fans: List[Tuple[Optional[int], Optional[int], complex, Dict[int, complex]]] = []
 
     def mul_phase(self, regs, w: complex) -> None:
         mask = sum(1 << k for k in regs)
@@ -783,12 +784,15 @@ class _Group:
                 self.tab[rho] *= w
         self.has_tab = True
 
-    def take_fixed(self, kt: int, entries: Dict[int, complex]) -> bool:
-        bits = self.fixed_bits + [q for q in entries if q not in self.fixed_bits]
+    def take_sel(self, kt: Optional[int], tsel: Optional[int], w0: complex, entries: Dict[int, complex]) -> bool:
+        """amp *= w0 * prod(entries whose selector bit is set) on the amplitudes with register bit kt set (kt None:
+        all of them), if the selector bit `tsel` is set (None: always)."""
+        want = ([tsel] if tsel is not None else []) + list(entries)
+        bits = self.sel_bits + [q for q in want if q not in self.sel_bits]
         if len(bits) > 3 or self.diag is not None:
             return False
-        self.fixed_bits = bits
-        self.fix_fans.append((kt, dict(entries)))
+        self.sel_bits = bits
+        self.sel_fans.append((kt, tsel, complex(w0), dict(entries)))
         self.has_tab = True
         return True
 
@@ -804,7 +808,7 @@ class _Group:
 
     def words_kw(self, prog: Program, r: int) -> Optional[dict]:
         kw: dict = {}
-        p = self.fixed_bits + [63] * (3 - len(self.fixed_bits))      # 63: no such bit (reads as 0 in every tile)
+        p = self.sel_bits + [63] * (3 - len(self.sel_bits))          # 63: no such selector (reads as 0)
         sel = (p[0] << 4) | (p[1] << 10)
         if self.sh:
             pay: List[complex] = []
@@ -814,18 +818,23 @@ class _Group:
             kw = dict(tk=T_LAYER, rm=sum(1 << k for k in self.sh) | sel, roff_t=prog.add_reals(pay))
         if self.has_tab:
             assert self.diag is None
-            tabs: List[complex] = []
-            for var in range(1 << len(self.fixed_bits)):
+            m = len(self.sel_bits)
+            tabs = np.ones((1 << self.r, 1 << m), dtype=complex)          # [rho][variant]
+            for var in range(1 << m):
+                on = {q for i, q in enumerate(self.sel_bits) if (var >> i) & 1}
                 t = self.tab.copy()
-                for kt, entries in self.fix_fans:
-                    f = 1.0 + 0j
+                for kt, tsel, w0, entries in self.sel_fans:
+                    if tsel is not None and tsel not in on:
+                        continue
+                    f = complex(w0)
                     for q, w in entries.items():
-                        if (var >> self.fixed_bits.index(q)) & 1:
+                        if q in on:
                             f *= w
                     for rho in range(1 << self.r):
-                        if (rho >> kt) & 1:
+                        if kt is None or (rho >> kt) & 1:
                             t[rho] *= f
-                tabs += list(t)
+                tabs[:, var] = t
+            tabs = list(tabs.reshape(-1))
             kw.update(dk=D_TAB, roff_d=prog.add_reals(tabs), fid=p[2])
             kw.setdefault("rm", sel)
         elif self.diag is not None:
@@ -1002,13 +1011,24 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int, direct_io: bool
                 touched = [kt]
                 if not entries and w0 == 1.0:
                     return
-            if kt is not None and entries and all(q not in loc for q in entries):
-                # constant per tile: a table variant instead of a record of its own, if the group has room
-                i = diag_min[kt]
-                if slot(i).take_fixed(kt, entries):
-                    slots[i].mul_fan(kt, w0, {})
-                    touch([kt], i)
-                    return
+            def selector(q: int) -> int:
+                if q in loc:
+                    return 48 + loc[q]
+                assert q < 48
+                return q
+
+            if all(reg_index(q) is None for q in entries):
+                # every other qubit is a thread bit or outside the tile: table variants instead of a record of its own
+                ents = {selector(q): w for q, w in entries.items()}
+                if kt is not None:
+                    i = diag_min[kt]
+                    if slot(i).take_sel(kt, None, w0, ents):
+                        touch([kt], i)
+                        return
+                else:
+                    for g2 in slots:
+                        if (g2.has_tab or g2.sh) and g2.take_sel(None, selector(t), w0, ents):
+                            return
             fixed = [(1 << q, w) for q, w in entries.items() if q not in loc]
             lw = {loc[q]: w for q, w in entries.items() if q in loc}
             attach(fan_fields(order, fixed, w0, lw, t), touched, max([diag_min[k] for k in touched] + [0]))
