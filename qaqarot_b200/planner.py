@@ -15,7 +15,9 @@ HBM-bound, so this planner trades sweeps for on-chip work in three steps:
    outside T are constant per tile).  Inside a pass gates are grouped into *rounds*: in a round each thread
    keeps 2^r amplitudes in registers (the round's r register bits) and applies the round's gates there.
    Commutation rule: two gates may be reordered unless they share a qubit on which one is non-diagonal.
-3. ``encode``: the descriptor words / payload reals documented in csrc/tile.cu.
+3. ``encode``: the descriptor words / payload reals documented in csrc/tile.cu.  Within a round the gates are
+   regrouped (commuting moves only) into few, fat records: up to four rotations per LAYER record, every diagonal on
+   the register bits in its table, diagonals that also involve up to three other bits as table variants (``_Group``).
 
 Rounding differs from the gate-by-gate reference only by the re-association of products (~1e-16 per fused
 gate), far inside the 1e-12 parity budget.
@@ -873,9 +875,6 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int, direct_io: bool
     def gate_words(tk=T_NONE, j=None, dk=D_NONE, fid=0, lm=0, rm=0, fm=0, roff_t=0, roff_d=0) -> List[int]:
         j = r if j is None else j
         return [tk | (j << 8) | (dk << 16) | (fid << 24) | (lm << 32) | (rm << 48), fm, roff_t | (roff_d << 32)]
-
-    def gate_words_kw(**kw) -> dict:
-        return kw
 
     def fan_fields(order, fid_entries, w0, lw, tgt) -> dict:
         """One fan: fixed (mask, w) entries, local per-bit factors `lw`, optional target qubit -> gate fields."""

@@ -254,3 +254,49 @@ def test_pass_overflow_falls_back_to_the_safe_payload_bound(monkeypatch):
     st = OracleState(n, 0)
     st.apply(prog)
     assert maxabs(st.download(), O.OracleBackend().run(circ.ops, n)) <= TOL
+
+
+def test_table_variants_absorb_phases_on_thread_and_fixed_bits():
+    """A CZ-like phase between a register bit and a thread bit / a bit outside the tile, and a 1-qubit phase on a
+    thread bit, become variants of the layer record's table (selectors 48 + local bit / physical bit) instead of
+    records of their own.  A hand-made round (register bits 4..7 of a 2^9 tile, 12 qubits) pins the encoding."""
+    from qaqarot_b200.program import Program
+    n, tile, reg = 12, list(range(9)), [4, 5, 6, 7]
+    rng = np.random.default_rng(11)
+    items, want_ops = [], []
+    for q in reg:
+        t = 0.3 + q
+        _, _, z, x, y, _ = P.split_shears(np.array([np.cos(t), -np.sin(t), np.sin(t), np.cos(t)], dtype=complex))
+        it = P.Item("mat", t=q, m=P.shear_matrix(z, x, y))
+        it.sh = (z, x, y)
+        items.append(it)
+        want_ops.append(("mat", q, P.shear_matrix(z, x, y)))
+    w = [np.exp(1j * a) for a in (0.4, 1.1, -0.8, 2.0)]
+    items += [P.Item("fan", t=4, w=1.0, entries={0: w[0]}),        # register bit x thread bit
+              P.Item("fan", t=11, w=1.0, entries={6: w[1]}),       # target outside the tile, entry on a register bit
+              P.Item("fan", t=1, w=w[2], entries={}),              # 1-qubit phase on a thread bit
+              P.Item("fan", t=5, w=w[3], entries={6: -1.0 + 0j})]  # register-local
+    prog = Program()
+    P.encode_pass(prog, P.Pass(tile, [P.Round(reg, items)]), n, 4, 4, False, True)
+    recs = _records(prog)
+    assert recs == [(P.T_LAYER, P.D_TAB)], recs
+    g0 = prog._words[(prog._words[3] >> 32) + 3]
+    sels = {((g0 >> 48) >> 4) & 63, ((g0 >> 48) >> 10) & 63, (g0 >> 24) & 0xFF}
+    assert sels == {48 + 0, 11, 48 + 1}, sels
+    psi = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
+    st = OracleState(n, 0)
+    st.upload(psi)
+    st.apply(prog)
+    idx = np.arange(2 ** n)
+    ref = psi.copy()
+    for _, q, m in want_ops:
+        i0 = idx[(idx >> q) & 1 == 0]
+        a0, a1 = ref[i0], ref[i0 | (1 << q)]
+        ref[i0], ref[i0 | (1 << q)] = m[0] * a0 + m[1] * a1, m[2] * a0 + m[3] * a1
+    bit = lambda q: (idx >> q) & 1 == 1
+    ref[bit(4) & bit(0)] *= w[0]
+    ref[bit(11) & bit(6)] *= w[1]
+    ref[bit(1)] *= w[2]
+    ref[bit(5)] *= w[3]
+    ref[bit(5) & bit(6)] *= -1
+    assert maxabs(st.download(), ref) <= 1e-13
