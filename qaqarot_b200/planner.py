@@ -1020,10 +1020,11 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int, direct_io: bool
                 # every other qubit is a thread bit or outside the tile: table variants instead of a record of its own
                 ents = {selector(q): w for q, w in entries.items()}
                 if kt is not None:
-                    i = diag_min[kt]
-                    if slot(i).take_sel(kt, None, w0, ents):
-                        touch([kt], i)
-                        return
+                    slot(diag_min[kt])
+                    for i in range(diag_min[kt], len(slots)):     # (a later existing group if this one is full)
+                        if slots[i].take_sel(kt, None, w0, ents):
+                            touch([kt], i)
+                            return
                 else:
                     for g2 in slots:
                         if (g2.has_tab or g2.sh) and g2.take_sel(None, selector(t), w0, ents):
