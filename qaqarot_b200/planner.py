@@ -55,7 +55,8 @@ class PlanConfig:
                               # ~7 ms of data movement at 30 qubits whatever it computes: measured 676 -> 645 ms
                               # on the 30-qubit random-layer circuit going from 150 to 300)
     scan_limit: int = 4096    # how far ahead of the first unscheduled item a pass may look
-    direct_io: bool = False   # let the FIRST round load straight from HBM (measured neutral at A = 12)
+    direct_io: bool = False   # flag the FIRST round as loadable straight from HBM (measured neutral at A = 12; the
+                              # kernel accepts the flag and ignores it since its code was removed, csrc/tile.cu)
     direct_out: bool = True   # let the LAST round store straight to HBM when its register bits avoid the row bits:
                               # the kernel then requests the next tile while that round's gates run
     kernel_tiles: Tuple[int, ...] = (9, 10, 11, 12, 13)   # tile sizes csrc/tile.cu instantiates (r = 4)
