@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--gpu", action="store_true")
     ap.add_argument("--cases", type=int, default=200)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--row-bits", type=int, default=4, help="--gpu: PlanConfig.c (low index bits in every tile)")
     ap.add_argument("--shots", action="store_true", help="fuzz measurement: mid-circuit measure / reset, seeded shot Counters")
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
@@ -36,7 +37,7 @@ def main():
         if args.gpu:
             n = int(rng.integers(9, 19))
             a = int(rng.integers(9, min(n, 13) + 1))
-            cfg = PlanConfig(a=a, max_cost=float(rng.choice([20, 150, 300])), direct_io=bool(rng.integers(2)),
+            cfg = PlanConfig(a=a, c=args.row_bits, max_cost=float(rng.choice([20, 150, 300])), direct_io=bool(rng.integers(2)),
                              direct_out=bool(rng.integers(2)))
             be = B200Backend(plan_config=cfg)
         else:
