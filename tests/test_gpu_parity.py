@@ -257,6 +257,52 @@ def test_tile_kernel_matches_descriptor_interpreter():
             assert maxabs(got, ref.psi) <= 1e-14
 
 
+@pytest.mark.parametrize("a", [9, 12])
+def test_layer_record_with_table_variants_matches_interpreter(a):
+    """A hand-made round: four rotations in one LAYER record whose table carries a register-local CZ and phase, and
+    three selector variants (a thread bit x register bit phase, a fixed-bit target with a register entry, a 1-qubit
+    phase on a thread bit); then a general 2x2 + fan record, so both kernel instantiations (with / without the general
+    target stages) run.  CUDA executor against the numpy interpreter on a dense random state."""
+    from oracle.program_interp import OracleState
+    from qaqarot_b200.device import DeviceState
+    from qaqarot_b200 import planner as P
+    from qaqarot_b200.program import Program
+    n = a + 3
+    rng = np.random.default_rng(90 + a)
+    reg = [4, 5, 6, 7]
+
+    def rot(q, t):
+        _, _, z, x, y, _ = P.split_shears(np.array([np.cos(t), -np.sin(t), np.sin(t), np.cos(t)], dtype=complex))
+        it = P.Item("mat", t=q, m=P.shear_matrix(z, x, y))
+        it.sh = (z, x, y)
+        return it
+
+    w = [np.exp(1j * x) for x in (0.4, 1.1, -0.8, 2.0)]
+    layer = [rot(q, 0.3 + q) for q in reg] + [
+        P.Item("fan", t=4, w=1.0, entries={0: w[0]}), P.Item("fan", t=a + 1, w=1.0, entries={6: w[1]}),
+        P.Item("fan", t=1, w=w[2], entries={}), P.Item("fan", t=5, w=w[3], entries={6: -1.0 + 0j}),
+        rot(4, -1.2), rot(7, 0.9)]
+    general = [P.Item("mat", t=5, m=np.array([0.6, 0.8j, 0.8j, 0.6], dtype=complex)),
+               P.Item("fan", t=5, w=w[0], entries={2: w[1], a + 2: w[2]}), P.Item("x", t=6, ctrls=(a,))]
+    for items, want_full in ((layer, False), (layer + general, True)):
+        prog = Program()
+        P.encode_pass(prog, P.Pass(list(range(a)), [P.Round(reg, items)]), n, 4, 4, False, True)
+        kinds = set()
+        pos = prog._words[3] >> 32
+        for g in range(prog._words[pos] & 0xFFFF):
+            kinds.add(prog._words[pos + 3 + 3 * g] & 0xFF)
+        assert (bool(kinds & {P.T_MATC, P.T_MATR, P.T_X})) == want_full and P.T_LAYER in kinds
+        psi = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
+        dev, ref = DeviceState(n), OracleState(n)
+        dev.upload(psi)
+        ref.upload(psi)
+        dev.apply(prog)
+        ref.apply(prog)
+        got = dev.download()
+        dev.close()
+        assert maxabs(got, ref.psi) <= 1e-13
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 10, 11, 14, 18, 21])
 def test_permute_kernel_against_interpreter(n):
     """In-place index-bit involutions (relabelled swap gates): random disjoint transpositions, bit reversal,
