@@ -34,10 +34,11 @@
 //     A record runs where the fixed-bit mask (per tile) and the thread mask (per thread) are satisfied:
 //     target stage on register bit j:  1 = complex 2x2 (8 reals, row major re/im), 2 = real 2x2 (same layout),
 //                                      3 = pair swap; pairs whose other register bits satisfy reg_mask
-//                                      6 = layer: for each register bit k in reg_mask the three in-place shears
-//                                          a0 += z a1; a1 += x a0; a0 += y a1 on the pairs of bit k, payload
-//                                          4 x (z, x, y, 0); j unused.  A real 2x2 up to row scalings, which the
-//                                          planner keeps as a pending diagonal on the wire (planner.split_shears)
+//                                      6 = layer: for each register bit k in reg_mask (bits 0..3) the three
+//                                          in-place shears a0 += z a1; a1 += x a0; a0 += y a1 on the pairs of bit
+//                                          k, payload 4 x (z, x, y, 0); j unused.  With z = y = -tan(t/2), x = sin t
+//                                          a rotation by t: the planner writes every 1-qubit unitary as
+//                                          phase . rotation . phase (planner.split_shears)
 //     diag stage:  1 / 2 = fan  amp *= fix[fan] * lane_t[lane] * warp_t[warp] (* reg_t[rho] for kind 2) on the
 //                  amplitudes with register bit j set (j = R: all); tables 32 + 2^(A-R-5) (+ 2^R) complex
 //                  3 = phase  amp *= reals[offset] where rho satisfies reg_mask (never fused with a target stage)
