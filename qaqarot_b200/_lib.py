@@ -14,6 +14,7 @@ from typing import List, Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libb200sv.so")
+ABI_VERSION = 101            # b200_version() of the library this planner's TILE descriptors are written for
 SOURCES = ["b200sv.cu", "sample.cu", "tile.cu", "permute.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -119,6 +120,10 @@ def load() -> C.CDLL:
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
+    if lib.b200_version() != ABI_VERSION:
+        raise B200LibraryError(
+            f"{LIB_PATH} reports version {lib.b200_version()}, this package needs {ABI_VERSION}: the library is stale, "
+            "rebuild it with `python -c 'import __graft_entry__ as g; g.build()'`")
     _lib = lib
     return lib
 

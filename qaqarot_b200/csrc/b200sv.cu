@@ -238,7 +238,7 @@ extern "C" {
 
 const char* b200_last_error(void) { return g_error.c_str(); }
 
-int b200_version(void) { return 100; }
+int b200_version(void) { return 101; }   // 101: TILE descriptors with layer / table records (tile.cu)
 
 int b200_device_count(int* out) {
   B200_REQUIRE(out != nullptr, "b200_device_count: null out");
