@@ -198,6 +198,14 @@ class OracleState:
                 out[g, 1] = prob[sel & (bit == 1)].sum()
         return out
 
+    def marginal(self, qubits):
+        qubits = [int(q) for q in qubits]
+        idx = np.arange(1 << len(qubits), dtype=np.uint64)
+        gb = np.zeros_like(idx)
+        for j, q in enumerate(qubits):
+            gb |= ((idx >> np.uint64(j)) & np.uint64(1)) << np.uint64(q)
+        return self.cond_probs(sum(1 << q for q in qubits), -1, gb)[:, 0].copy()
+
     def expect_group(self, xmask, zymasks, coeffs):
         idx = np.arange(self.dim, dtype=np.int64)
         w = np.zeros(self.dim, dtype=complex)

@@ -509,3 +509,20 @@ def expectation(terms, psi: np.ndarray) -> float:
     for coeff, letters in terms:
         acc += coeff * np.vdot(psi, pauli_apply(letters, psi))
     return float(acc.real)
+
+
+
+def expect_marginal(psi: np.ndarray, meas) -> dict:                     # vqe.py:231-252 (`expect`)
+    """{outcome tuple over `meas`: probability}, as blueqat's non-sampling VQE sampler computes it from a
+    statevector: amplitudes of probability exactly 0 are skipped, so outcomes that never occur have no key."""
+    meas = tuple(int(m) for m in meas)
+    mask = 0
+    for m in meas:
+        mask |= 1 << m
+    prob = psi.real ** 2 + psi.imag ** 2
+    out: dict = {}
+    for i in np.nonzero(prob)[0]:
+        k = int(i) & mask
+        key = tuple(1 if k & (1 << m) else 0 for m in meas)
+        out[key] = out.get(key, 0.0) + float(prob[i])
+    return out

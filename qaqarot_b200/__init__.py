@@ -8,7 +8,8 @@ from .backend import B200Backend, ShardedB200Backend
 from .circuit import BackendRegistry, Circuit
 from .pauli import I, X, Y, Z
 from .register import register
+from . import samplers
 
-__all__ = ["B200Backend", "ShardedB200Backend", "BackendRegistry", "Circuit", "X", "Y", "Z", "I", "register"]
+__all__ = ["B200Backend", "ShardedB200Backend", "BackendRegistry", "Circuit", "X", "Y", "Z", "I", "register", "samplers"]
 
 register()

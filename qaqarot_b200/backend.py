@@ -413,6 +413,19 @@ class B200Backend(_Base):
         return expectation_on_state(ctx.device_state, terms)
 
 
+    def marginal(self, gates, n_qubits, meas, initial: Optional[np.ndarray] = None) -> Dict[Tuple[int, ...], float]:
+        """{outcome of the qubits `meas`: probability} of the final state, reduced on the device (what
+        ``vqe.expect(circuit.run(), meas)`` computes on the host, vqe.py:231-259; see samplers.py)."""
+        from .samplers import expect_on_state
+        for q in meas:
+            if not 0 <= int(q) < n_qubits:
+                raise ValueError(f"measured qubit {q} outside the {n_qubits}-qubit register")
+        if initial is not None:
+            initial = _check_initial(initial, n_qubits)
+        ctx = self._execute(gates, n_qubits, 1, initial, False, True, use_backend_cache=initial is None)
+        return expect_on_state(ctx.device_state, meas)
+
+
 def expectation_on_state(st, terms) -> float:
     groups: Dict[int, Tuple[List[int], List[complex]]] = {}
     for coeff, letters in terms:

@@ -182,6 +182,11 @@ class DeviceState:
                                              out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def marginal(self, qubits: Sequence[int]) -> np.ndarray:
+        """Probabilities of the 2^k outcomes of the distinct `qubits` (bit j of the index = qubits[j]): one
+        reduction over the state, nothing but 2^k doubles comes back (samplers.py)."""
+        return marginal_from_cond_probs(self, qubits)
+
     # -- timing (bench.py / profiling) ------------------------------------------------------------
     def event_record(self, slot: int) -> None:
         _lib.check(self._lib.b200_event_record(self._h, slot))
@@ -190,6 +195,18 @@ class DeviceState:
         ms = C.c_double()
         _lib.check(self._lib.b200_event_elapsed_ms(self._h, slot_a, slot_b, C.byref(ms)))
         return ms.value
+
+
+def marginal_from_cond_probs(st, qubits: Sequence[int]) -> np.ndarray:
+    """Marginal distribution through `st.cond_probs` (any state object with that method): every outcome is one
+    group of the reduction."""
+    qubits = [int(q) for q in qubits]
+    assert len(set(qubits)) == len(qubits) and len(qubits) <= 24
+    idx = np.arange(1 << len(qubits), dtype=np.uint64)
+    gb = np.zeros_like(idx)
+    for j, q in enumerate(qubits):
+        gb |= ((idx >> np.uint64(j)) & np.uint64(1)) << np.uint64(q)
+    return st.cond_probs(sum(1 << q for q in qubits), -1, gb)[:, 0].copy()
 
 
 class PinnedBuffer:

@@ -471,6 +471,23 @@ class ShardedState:
             fixed_mask |= tbit
         return out
 
+    def marginal(self, wires: Sequence[int]) -> np.ndarray:
+        """Probabilities of the 2^k outcomes of the distinct `wires` (bit j of the index = wires[j]): each rank
+        reduces the outcomes compatible with its shard number, the partial tables are added over the ranks."""
+        bits = [self.layout[int(w)] for w in wires]
+        lmask = (1 << self.n_local) - 1
+        idx = np.arange(1 << len(bits), dtype=np.uint64)
+        gb = np.zeros_like(idx)
+        for j, b in enumerate(bits):
+            gb |= ((idx >> np.uint64(j)) & np.uint64(1)) << np.uint64(b)
+        mask = sum(1 << b for b in bits)
+        mine = (self.rank << self.n_local) & mask
+        here = np.nonzero((gb & np.uint64(mask & ~lmask)) == np.uint64(mine))[0]
+        table = np.zeros(idx.size)
+        if here.size:
+            table[here] = self.st.cond_probs(mask & lmask, -1, gb[here] & np.uint64(lmask))[:, 0]
+        return self._allreduce(table)
+
     def expect_group(self, xmask: int, zymasks: Sequence[int], coeffs: Sequence[complex]) -> complex:
         wires = [w for w in range(self.n_qubits) if (xmask >> w) & 1]
         self._make_local(wires)                                 # X / Y pair amplitudes inside one shard only

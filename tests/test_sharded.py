@@ -82,6 +82,11 @@ def _worker(rank, world, port, errors):
         terms = [(1.0, [("Z", 0), ("Z", 8)]), (0.5, [("Z", 7), ("Z", 8)]), (0.25, [("Z", 3)]),
                  (-1.5, [("X", 8), ("Y", 2)]), (0.75, [("Y", 7), ("Y", 8), ("Z", 0)]), (2.0, [])]
         assert abs(circ.run(backend=be, hamiltonian=h) - O.expectation(terms, psi)) < 1e-10
+        # 5. marginal distribution of measured wires (global and local), the non-sampling VQE sampler
+        for meas in ((8, 2, 0), (7,), (1, 8, 8, 3)):
+            want = O.expect_marginal(psi, meas)
+            got = be.marginal(circ.ops, n, meas)
+            assert all(abs(got.get(k, 0.0) - want.get(k, 0.0)) < 1e-13 for k in set(got) | set(want)), meas
         dist.barrier()
         dist.destroy_process_group()
     except Exception:
