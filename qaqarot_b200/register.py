@@ -8,13 +8,16 @@ from __future__ import annotations
 
 from .backend import B200Backend
 from .circuit import BACKENDS, BackendRegistry
+from .transpile import FuseTranspiler
 
 NAME = "b200"
+FUSE_NAME = "b200_fuse"          # transpiler backend: run() returns the planner's normal form as a circuit
 
 
 def register(name: str = NAME, allow_overwrite: bool = True) -> bool:
     """Returns True when blueqat was found and the backend registered there as well."""
     BackendRegistry.register_backend(name, B200Backend, allow_overwrite=True)
+    BackendRegistry.register_backend(FUSE_NAME, FuseTranspiler, allow_overwrite=True)
     try:
         from blueqat import BlueqatGlobalSetting
         from blueqat.backends import BACKENDS as BQ
@@ -26,4 +29,5 @@ def register(name: str = NAME, allow_overwrite: bool = True) -> bool:
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         BlueqatGlobalSetting.register_backend(name, B200Backend, allow_overwrite=True)
+        BlueqatGlobalSetting.register_backend(FUSE_NAME, FuseTranspiler, allow_overwrite=True)
     return True
