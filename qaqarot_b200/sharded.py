@@ -221,6 +221,41 @@ class ShardedState:
             return out
         return np.ascontiguousarray(res)
 
+    # -- checkpoints (a 33-36 qubit state cannot return through one ndarray) -------------------
+    CHECKPOINT_FORMAT = "b200sv-sharded-v1"
+
+    def save(self, directory: str) -> None:
+        """Every rank writes its shard as raw little-endian complex128 (`shard_<rank>.c128`, physical index order);
+        rank 0 writes `header.json` with the register size, the world size and the wire -> index-bit layout, without
+        which the shards cannot be interpreted (swap gates and exchanges only relabel wires)."""
+        import json
+        import os
+        _, dist = _torch()
+        if self.rank == 0:
+            os.makedirs(directory, exist_ok=True)
+        dist.barrier(group=self.group)
+        self.st.download().astype("<c16", copy=False).tofile(os.path.join(directory, f"shard_{self.rank}.c128"))
+        if self.rank == 0:
+            with open(os.path.join(directory, "header.json"), "w") as f:
+                json.dump({"format": self.CHECKPOINT_FORMAT, "n_qubits": self.n_qubits, "world": self.world,
+                           "n_local": self.n_local, "dtype": "complex128", "byteorder": "little",
+                           "layout_wire_to_index_bit": list(self.layout)}, f)
+        dist.barrier(group=self.group)
+
+    def load(self, directory: str) -> None:
+        """Restore a checkpoint written by `save` on the same world size (shards are not re-cut)."""
+        import json
+        import os
+        with open(os.path.join(directory, "header.json")) as f:
+            h = json.load(f)
+        if h.get("format") != self.CHECKPOINT_FORMAT or h["n_qubits"] != self.n_qubits or h["world"] != self.world:
+            raise ValueError(f"checkpoint {directory} does not match this register: {h}")
+        shard = np.fromfile(os.path.join(directory, f"shard_{self.rank}.c128"), dtype="<c16")
+        if shard.size != 1 << self.n_local:
+            raise ValueError(f"shard_{self.rank}.c128 has {shard.size} amplitudes, expected {1 << self.n_local}")
+        self.st.upload(shard.astype(np.complex128, copy=False))
+        self.layout = [int(b) for b in h["layout_wire_to_index_bit"]]
+
     def copy_from(self, other: "ShardedState") -> None:
         self.st.copy_from(other.st)
         self.layout = list(other.layout)

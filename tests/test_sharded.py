@@ -87,6 +87,19 @@ def _worker(rank, world, port, errors):
             want = O.expect_marginal(psi, meas)
             got = be.marginal(circ.ops, n, meas)
             assert all(abs(got.get(k, 0.0) - want.get(k, 0.0)) < 1e-13 for k in set(got) | set(want)), meas
+        # 6. checkpoint: shards + header with the wire layout, restored into a fresh register
+        import tempfile
+        from qaqarot_b200.sharded import ShardedState
+        circ = C.build(Circuit, {"n": n, "ops": C.random_ops(rng, n, 50, True)}).swap[0, 8].h[8]
+        want = oracle(circ)
+        ctx = be._execute(circ.ops, n, 1, None, False, True)
+        path = [tempfile.mkdtemp() if rank == 0 else None]
+        dist.broadcast_object_list(path, src=0)
+        ctx.device_state.save(path[0])
+        fresh = ShardedState(n, host_state_factory=lambda nl, off: OracleState(nl, 0, off))
+        fresh.load(path[0])
+        assert fresh.layout == ctx.device_state.layout
+        assert np.abs(fresh.download() - want).max() <= 1e-12
         dist.barrier()
         dist.destroy_process_group()
     except Exception:
