@@ -24,6 +24,7 @@ gate), far inside the 1e-12 parity budget.
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass, field
 from typing import Dict, FrozenSet, List, Optional, Sequence, Tuple
 
@@ -161,30 +162,29 @@ def split_shears(m) -> Optional[Tuple[complex, complex, float, float, float, com
     phase and is absorbed by the next gate on the wire).  A real rotation keeps dl = dr = 1; a real reflection
     (H) is a rotation times Z, dl = -1.
     Returns (g, dl, z, x, y, dr), or None when the pieces do not reproduce `m` to rounding (not unitary)."""
-    m = np.asarray(m, dtype=complex).reshape(4)
-    if not np.all(np.isfinite(m)):
+    a, b, c, d = (complex(v) for v in np.asarray(m).reshape(4))          # (plain Python arithmetic: this runs once
+    if not all(math.isfinite(v.real) and math.isfinite(v.imag) for v in (a, b, c, d)):     # per gate of a circuit)
         return None
-    a, b, c, d = (complex(v) for v in m)
     if c == 0 or b == 0:
         return None                               # diagonal matrices never get here; anything else is not unitary
-    if np.all(m.imag == 0):
+    if a.imag == 0 and b.imag == 0 and c.imag == 0 and d.imag == 0:
         det = a.real * d.real - b.real * c.real
         dl = 1.0 + 0j if det > 0 else -1.0 + 0j   # m = diag(1, dl) . R
-        theta = np.arctan2(c.real * dl.real, a.real)
+        theta = math.atan2(c.real * dl.real, a.real)
         g, dr = 1.0 + 0j, 1.0 + 0j
-        if abs(theta) > np.pi / 2:                 # R(theta) = -R(theta -+ pi)
-            theta -= np.copysign(np.pi, theta)
+        if abs(theta) > math.pi / 2:               # R(theta) = -R(theta -+ pi)
+            theta -= math.copysign(math.pi, theta)
             g = -1.0 + 0j
     else:
-        theta = np.arctan2(abs(c), abs(a))         # in [0, pi/2]
+        theta = math.atan2(abs(c), abs(a))         # in [0, pi/2]
         g = _unit(a) if a != 0 else 1.0 + 0j
         dr = -_unit(b) / g
         # the phases are read off the LARGE entries (those of small ones are only known to ~eps / |entry|)
         dl = _unit(d) / (g * dr) if abs(a) >= abs(c) else _unit(c) / g
-    z, x = -np.tan(theta / 2.0), np.sin(theta)
-    sm = shear_matrix(z, x, z)
-    rec = g * np.array([sm[0], sm[1] * dr, dl * sm[2], dl * sm[3] * dr])
-    if np.max(np.abs(rec - m)) > 2e-15:
+    z, x = -math.tan(theta / 2.0), math.sin(theta)
+    s00, s01, s10, s11 = 1.0 + x * z, z + z * (1.0 + x * z), x, 1.0 + x * z          # shear_matrix(z, x, z)
+    err = max(abs(g * s00 - a), abs(g * s01 * dr - b), abs(g * dl * s10 - c), abs(g * dl * s11 * dr - d))
+    if not err <= 2e-15:
         return None
     return g, dl, float(z), float(x), float(z), dr
 
