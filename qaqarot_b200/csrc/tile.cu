@@ -5,12 +5,27 @@
 //
 // Data layout.  A pass owns A index bits `tile[0..A)` (ascending physical positions; tile[i] = i for i < c so
 // that 2^c amplitudes = 2^c * 16 B are contiguous in HBM).  Tile number t in [0, 2^(n-A)) has its bits spread
-// over the remaining index positions; a CTA copies the 2^A amplitudes of its tile to shared memory with
-// 16-byte cp.async (coalesced rows), runs the pass's rounds, and streams the tile back with 16-byte stores.
-// Shared-memory slot of local index l is swz(l) = l ^ xor of l's higher 3-bit groups folded into bits 0..2:
-// GF(2)-linear, so swz(thread part | register part) = swz(thread) ^ swz(register), and a quarter warp's eight
-// 16-byte accesses fall into eight different 16-byte bank groups whenever the thread bits mapped to lane bits
-// 0..2 have distinct positions mod 3 (the planner orders them so).
+// over the remaining index positions.
+//
+// Data movement (round 2; tools/tma_probe.cu and profiles/r02_tma_probe.json are the measurements behind it).
+// One persistent CTA per SM: two groups of 2^(A-4) compute threads and a ring of three tile buffers in shared
+// memory.  The state is described to the TMA unit as a rank-5 tensor of doubles whose
+// dimensions are the runs of tile bits (each followed by the non-tile bits above it, see build_tile_map), so a
+// whole tile is ONE cp.async.bulk.tensor per direction (row-granular cp.async.bulk copies retire at one per ~31
+// cycles per SM whatever their size and cannot carry 256-byte rows).  The groups take alternate tiles (tile j of
+// the CTA: group j % 2, buffer j % 3), so one computes while the other waits or stores and a third tile is always
+// in flight: a finished tile leaves through a TMA store issued by warp 0 of its group, and as soon as that store
+// has read the buffer the same warp requests the tile that uses the buffer next (j + 3, for the OTHER group).
+// There is no producer warp: 2 x 256 threads leave 128 registers per thread (a 17th warp rounds the allocation up
+// to 640 threads and 96 registers).  mbarriers: full[stage][use & 1] with the TMA transaction count -- two per
+// stage because the groups use a stage alternately and a parity wait is only valid for a waiter that consumed the
+// barrier's previous phase itself (tools/tma_probe.cu has the story); no `empty` barriers are needed because the
+// thread that refills a buffer is the one that waited for its store.
+// Shared-memory slot of local index l is swz(l) = l ^ ((l >> 3) & 7), the TMA unit's SWIZZLE_128B pattern for
+// 16-byte elements: GF(2)-linear, so swz(thread part | register part) = swz(thread) ^ swz(register), and a
+// quarter warp's eight 16-byte accesses fall into eight different 16-byte bank groups whenever the thread bits
+// mapped to lane bits 0..2 are one each of the local bit pairs (0,3), (1,4), (2,5) (the planner orders them so
+// and keeps both bits of a pair out of one round's register set when it can).
 //
 // Rounds.  In a round every thread holds 2^R amplitudes in registers: the R *register bits* (local bit
 // positions order[0..R)) enumerate them, the thread index supplies the other A-R local bits through
@@ -21,9 +36,8 @@
 //
 // Descriptor (uint64 words, produced by qaqarot_b200/planner.py::encode_pass; `reals` = float64 pool):
 //   D[0] = A | c<<8 | R<<16 | n_rounds<<24 | n_fans<<32 | flags<<40   D[1], D[2] = tile bit positions, 8 bits each
-//          flags: 2 = the last round stores straight to HBM (its register bits avoid the c row bits, so a half
-//          warp still covers one contiguous 2^c * 16 B row); 1 = same for the first round's loads: accepted and
-//          ignored (measured neutral; the code was removed to keep the kernel small)
+//          flags 1, 2 (first / last round straight from / to HBM, round 1): accepted and ignored -- with the TMA
+//          pipeline a store from the register tile is slower than the TMA store (profiles/r02_tma_probe.json)
 //   D[3] = fan directory offset | rounds offset << 32      D[4] = first payload real | payload length << 32
 //          (everything the pass reads from `reals` is that one range; each CTA keeps a copy in shared memory)
 //   fan directory: n_fans word offsets; fan record: n_entries | roff<<32, then n_entries masks.
@@ -52,6 +66,8 @@
 //     A 2x2 followed by a fan on the same register bit (the H + controlled-phase ladder of a QFT) is one record.
 #include "common.cuh"
 
+#include <cuda.h>
+
 #include <cstdio>
 #include <cstdlib>
 
@@ -61,20 +77,38 @@ constexpr int kMaxFans = 64;
 constexpr int T_NONE = 0, T_MATC = 1, T_MATR = 2, T_X = 3, T_LAYER = 6;
 constexpr int D_NONE = 0, D_FANT = 1, D_FAN = 2, D_PHASE = 3, D_W = 4, D_FIX = 5, D_TAB = 6;
 
-__device__ __forceinline__ uint32_t swz(uint32_t l) {
-  return l ^ ((l >> 3) & 7u) ^ ((l >> 6) & 7u) ^ ((l >> 9) & 7u) ^ ((l >> 12) & 7u);
-}
-__host__ __device__ constexpr uint32_t swz_c(uint32_t l) {
-  return l ^ ((l >> 3) & 7u) ^ ((l >> 6) & 7u) ^ ((l >> 9) & 7u) ^ ((l >> 12) & 7u);
-}
+__host__ __device__ __forceinline__ uint32_t swz(uint32_t l) { return l ^ ((l >> 3) & 7u); }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+// ---- mbarrier / TMA primitives (PTX) -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sptr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sptr(b)), "r"(count));
 }
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sptr(b)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sptr(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+               "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(sptr(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load5(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, const int (&c)[5]) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(sptr(smem_dst)), "l"(tm), "r"(sptr(bar)), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]) : "memory");
+}
+__device__ __forceinline__ void tma_store5(const CUtensorMap* tm, const void* smem_src, const int (&c)[5]) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(tm), "r"(sptr(smem_src)), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+template <int NT>
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(NT) : "memory"); }
 
 __host__ __device__ constexpr int ctz_c(int i) { return (i & 1) ? 0 : (i & 2) ? 1 : (i & 4) ? 2 : (i & 8) ? 3 : 4; }
 
@@ -281,13 +315,16 @@ __device__ __forceinline__ void run_diag(c128 (&v)[1 << R], uint32_t key2, uint3
 // ---- pre-decoded pass (built once per CTA in shared memory) ------------------------------------------------------
 // Decoding the planner's descriptor per gate, per thread, per tile cost ~60 instructions a gate in the first
 // version (ncu source view: a quarter of all issue slots).  The gate list is the same for every tile, so each
-// CTA decodes it once into 32-byte records and per-thread / per-round tables, and the tile loop only reads them.
+// CTA decodes it once into 16-byte records and per-thread / per-round tables, and the tile loop only reads them.
 constexpr int kMaxGates = 160;     // per pass
-constexpr int kMaxRounds = 8;
+constexpr int kMaxRounds = 6;     // planner.PlanConfig.max_rounds
 constexpr int kSpreadTabs = 5;     // 6 bits of the tile number each: up to 30 non-tile index bits
+constexpr int kStages = 3;         // tile buffers in the ring
+constexpr int kGroups = 2;         // compute groups taking alternate tiles
+constexpr int R = 4;               // register bits per round (2^R amplitudes per thread)
 
 constexpr int kMaxPayload = 2560;  // float64 payload of one pass kept in shared memory (planner.MAX_PAYLOAD)
-constexpr int kMaxFanWords = 512;  // directory + records of the pass's fans (planner keeps a pass below this)
+constexpr int kMaxFanWords = 512;  // fan directory + records of the pass's fans (planner keeps a pass below this)
 // record (one uint4): x = key1 | key2<<8 | fan<<16 | fixed mask bits 32..39<<24
 //                     y = thread mask | reg mask<<16    z = target payload | diag payload<<16 (complex units, relative)
 //                     w = fixed mask bits 0..31
@@ -298,40 +335,44 @@ struct RoundHdr {                  // 16 bytes
   uint32_t pad;
 };
 
-template <int A, int R>
+// How a tile maps to the tensor the TMA unit sees (kernel parameter, built by build_tile_map).
+struct TileMapDev {
+  int32_t shift[5];                // index bit where field i starts (field 0 starts at the re/im bit: shift[0] = 0)
+  int32_t width[5];                // index bits the field spans (0: unused dimension)
+  int32_t n_sub_bits;              // top local bits enumerated by separate copies (more than 5 runs of tile bits)
+  int32_t sub_pos[9];              // ... their index positions
+  uint32_t sub_amps;               // amplitudes per copy
+};
+
+template <int A>
 struct TileSmem {
-  c128 tile[1 << A];
-  c128 fix[2][kMaxFans];           // per-tile fan products, two generations: no barrier separates the last round of
-                                   // a tile from the head of the next one when that round stores straight to HBM
+  c128 stage[kStages][1 << A];     // 1024-byte aligned (SWIZZLE_128B atoms): first member of the dynamic allocation
+  c128 fix[kGroups][kMaxFans];     // per-tile fan products, one set per compute group
   uint64_t spread[kSpreadTabs][64];
   uint4 rec[kMaxGates + 1];
   double pay[kMaxPayload];         // the pass's matrices, phases and fan tables
   uint64_t fanw[kMaxFanWords];     // fan directory and records (entry counts, payload offsets, fixed-bit masks)
   RoundHdr rh[kMaxRounds];
-  uint32_t thr[kMaxRounds][1 << (A - R)];   // per round, per thread: local index bits | swizzled byte offset / 16 << 16
+  uint16_t thr[kMaxRounds][1 << (A - R)];   // per round, per thread: its local index bits
   uint32_t round_off[kMaxRounds];
-  // direct global <-> register access of the first / last round (when its register bits avoid the row bits):
-  uint64_t gthr[1 << (A - R)];     // per thread: where its thread bits sit in the index space
-  uint64_t ghb[4];                 // per register bit: its index bit as a mask
+  uint64_t full[kStages][2];       // the tile's TMA load has landed; index = use of the stage & 1
 };
 
 // ---- the kernel ------------------------------------------------------------------------------------------------
 // FULL = false leaves out the general target stages (complex / real 2x2, pair swap, their controlled forms): a pass
-// of 1-qubit unitaries and phases needs none of them, and the kernel without their 24 unrolled bodies (4100 instead
-// of 6900 instructions) runs every record ~0.03 ms faster at 28 qubits -- measured 45.2 -> 41.0 ms on the 30-qubit QFT.
-template <int A, int R, int MINB, bool TIMING, bool FULL>
-__global__ void __launch_bounds__(1 << (A - R), MINB)
-k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const uint64_t* __restrict__ desc,
-       const double* __restrict__ reals, unsigned long long* __restrict__ phase_cycles, uint32_t flags,
+// of 1-qubit unitaries and phases needs none of them, and the kernel without their 24 unrolled bodies runs every
+// record faster (round 1: 45.2 -> 41.0 ms on the 30-qubit QFT).
+template <int A, bool FULL>
+__global__ void __launch_bounds__(kGroups * (1 << (A - R)), 1)
+k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMapDev tm, uint64_t n_tiles,
+       uint64_t index_offset, const uint64_t* __restrict__ desc, const double* __restrict__ reals, uint32_t flags,
        uint64_t init_tile, uint32_t init_local) {
-  static_assert(R == 3 || R == 4, "the record dispatch handles 3 or 4 register bits");
   constexpr int NT = 1 << (A - R), PER = 1 << R, NTB = A - R;
   constexpr int NWARP_T = (NTB > 5) ? (1 << (NTB - 5)) : 1;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  TileSmem<A, R>& S = *reinterpret_cast<TileSmem<A, R>*>(smem_raw);
-  c128* const sm = S.tile;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  TileSmem<A>& S = *reinterpret_cast<TileSmem<A>*>(smem_raw);
 
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t tid = threadIdx.x;
   const uint64_t h0 = desc[0], tb_lo = desc[1], tb_hi = desc[2];
   const int n_rounds = (int)((h0 >> 24) & 0xFF), n_fans = (int)((h0 >> 32) & 0xFF);
   const uint32_t dir_off = (uint32_t)(desc[3] & 0xFFFFFFFFu), rounds_off = (uint32_t)(desc[3] >> 32);
@@ -339,11 +380,9 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
   // flags bit 1: the state is a basis vector that nobody has written yet -- every tile is all zeros except
   // tile `init_tile`, whose local index `init_local` holds 1 (B200_OP_INIT folded into this pass)
   const bool init = (flags & 2u) != 0;
-  // (flag 1, "first round loads straight from HBM", is accepted and ignored: measured neutral, and its code cost
-  // every record ~0.01 ms -- see the note on kernel size at k_tile)
-  const bool direct_out = ((h0 >> 41) & 1) != 0;
+  const int n_sub = 1 << tm.n_sub_bits;
 
-  // ---- one-time setup ----------------------------------------------------------------------------------------
+  // ---- one-time setup ---------------------------------------------------------------------------------------
   if (tid == 0) {
     uint32_t pos = rounds_off, first = 0;
     for (int rd = 0; rd < n_rounds; ++rd) {
@@ -354,10 +393,15 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
       first += (uint32_t)(rh & 0xFFFF);
       pos += (uint32_t)(rh >> 16);
     }
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&S.full[s][0], 1);
+      mbar_init(&S.full[s][1], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (uint32_t i = tid; i < pay_len; i += NT) S.pay[i] = reals[pay_lo + i];
-  for (uint32_t i = dir_off + tid; i < rounds_off; i += NT) S.fanw[i - dir_off] = desc[i];
-  for (uint32_t idx = tid; idx < kSpreadTabs * 64; idx += NT) {
+  for (uint32_t i = tid; i < pay_len; i += blockDim.x) S.pay[i] = reals[pay_lo + i];
+  for (uint32_t i = dir_off + tid; i < rounds_off; i += blockDim.x) S.fanw[i - dir_off] = desc[i];
+  for (uint32_t idx = tid; idx < kSpreadTabs * 64; idx += blockDim.x) {
     uint64_t x = (uint64_t)(idx & 63u) << (6 * (idx >> 6));
     for (int i = 0; i < A; ++i) x = insert_zero(x, byte_of(tb_lo, tb_hi, i));
     S.spread[idx >> 6][idx & 63u] = x;
@@ -366,18 +410,14 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
   for (int rd = 0; rd < n_rounds; ++rd) {
     const uint64_t* __restrict__ rp = desc + S.round_off[rd];
     const uint64_t o_lo = rp[1], o_hi = rp[2];
-    uint32_t lt = 0;
-    for (int b = 0; b < NTB; ++b) lt |= ((tid >> b) & 1u) << byte_of(o_lo, o_hi, R + b);
-    S.thr[rd][tid] = lt | (swz(lt) << 16);
-    if (rd == n_rounds - 1) {      // the last round may store straight to HBM (flag 2)
-      uint64_t go = 0;
-      for (int b = 0; b < A; ++b) go |= (uint64_t)((lt >> b) & 1u) << byte_of(tb_lo, tb_hi, b);
-      S.gthr[tid] = go;
-      if (tid < R) S.ghb[tid] = 1ull << byte_of(tb_lo, tb_hi, byte_of(o_lo, o_hi, tid));
+    for (uint32_t t = tid; t < (uint32_t)NT; t += blockDim.x) {
+      uint32_t lt = 0;
+      for (int b = 0; b < NTB; ++b) lt |= ((t >> b) & 1u) << byte_of(o_lo, o_hi, R + b);
+      S.thr[rd][t] = (uint16_t)lt;
     }
     if (tid < R) S.rh[rd].srb[tid] = (uint16_t)swz(1u << byte_of(o_lo, o_hi, tid));
     const int ng = S.rh[rd].n_gates, first = S.rh[rd].first;
-    for (int gi = tid; gi < ng; gi += NT) {
+    for (int gi = tid; gi < ng; gi += blockDim.x) {
       const uint64_t g0 = rp[3 + 3 * gi], fm = rp[4 + 3 * gi], roffs = rp[5 + 3 * gi];
       const uint32_t tk = (uint32_t)(g0 & 0xFF), j = (uint32_t)((g0 >> 8) & 0xFF), dk = (uint32_t)((g0 >> 16) & 0xFF);
       const uint32_t fan = (uint32_t)((g0 >> 24) & 0xFF);
@@ -391,11 +431,6 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
                                      lm | (rm << 16), pt | (pd << 16), (uint32_t)fm);
     }
   }
-  // copy phases: thread handles local indices l = i * NT + tid; off_t / hb[] deposit l into index positions
-  uint64_t off_t = 0;
-#pragma unroll
-  for (int b = 0; b < NTB; ++b) off_t |= (uint64_t)((tid >> b) & 1u) << byte_of(tb_lo, tb_hi, b);
-  const uint32_t sw_t = swz(tid) << 4;              // byte offset of this thread's slot for i = 0
   __syncthreads();
 
   auto spread_tile = [&](uint64_t t) -> uint64_t {
@@ -404,49 +439,47 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
     for (int j = 1; j < kSpreadTabs; ++j) b |= S.spread[j][(t >> (6 * j)) & 63u];
     return b;
   };
+  // tensor coordinates (in doubles) of sub-copy `sub` of the tile whose non-tile index bits are `base`
+  auto coords = [&](uint64_t base, int sub, int (&c)[5]) {
+    for (int k = 0; k < tm.n_sub_bits; ++k)
+      if ((sub >> k) & 1) base |= 1ull << tm.sub_pos[k];
+    c[0] = (int)((base & ((1ull << tm.width[0]) - 1ull)) << 1);
+#pragma unroll
+    for (int i = 1; i < 5; ++i) c[i] = (int)((base >> tm.shift[i]) & ((1ull << tm.width[i]) - 1ull));
+  };
 
-  // B200_TILE_TIMING=1: warp 0 / lane 0 of every CTA accumulates the cycles it spends in each phase of a tile
-  long long tk0 = TIMING ? clock64() : 0;
-  auto tick = [&](int phase) {
-    if (TIMING && tid == 0) {
-      const long long now = clock64();
-      atomicAdd(phase_cycles + phase, (unsigned long long)(now - tk0));
-      tk0 = now;
+  // ---- compute groups ----------------------------------------------------------------------------------------
+  const uint32_t g = tid / NT, t = tid % NT, lane = t & 31u, warp = t >> 5;
+  c128* const fixp = S.fix[g];
+  unsigned char* const pay_b = reinterpret_cast<unsigned char*>(S.pay);
+  // request tile j of this CTA into its buffer (warp 0 of a group; lanes = sub-copies)
+  auto request = [&](uint32_t j) {
+    const uint64_t tile = blockIdx.x + (uint64_t)j * gridDim.x;
+    if (tile >= n_tiles) return;
+    const uint32_t s = j % kStages, u = j / kStages;
+    uint64_t* const fb = &S.full[s][u & 1u];
+    if (lane == 0) mbar_expect_tx(fb, 16u << A);
+    __syncwarp();
+    const uint64_t base = spread_tile(tile);
+    for (int sub = (int)lane; sub < n_sub; sub += 32) {
+      int c[5];
+      coords(base, sub, c);
+      tma_load5(S.stage[s] + (size_t)sub * tm.sub_amps, &tmap, fb, c);
     }
   };
-  // flags bit 2 (with a direct last round): the next tile's cp.async is issued as soon as every warp has taken
-  // the last round's amplitudes out of shared memory, so its HBM latency hides under that round's gates
-  const bool overlap = (flags & 4u) != 0 && direct_out && !init;
-  bool loaded = false;
-  uint32_t parity = 0;
-  for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, parity ^= 1u) {
-    c128* const fixp = S.fix[parity];
-    const uint64_t base = spread_tile(tile);
-    const uint64_t fixedidx = base | index_offset;
+  if (!init && tid < 32) {          // prologue: the first three tiles
+    for (uint32_t j = 0; j < (uint32_t)kStages; ++j) request(j);
+  }
+  bool store_pending = false;       // warp 0: the previous tile's store has not been waited for yet
+  uint32_t j_prev = 0;
+  for (uint32_t j = g;; j += kGroups) {
+    const uint64_t tile = blockIdx.x + (uint64_t)j * gridDim.x;
+    if (tile >= n_tiles) break;
+    // an initial pass synthesises its tiles and never shares a buffer between the groups
+    const uint32_t s = init ? g : j % kStages, u = j / kStages;
+    const uint64_t fixedidx = spread_tile(tile) | index_offset;
     const uint32_t fx_lo = (uint32_t)fixedidx, fx_hi = (uint32_t)(fixedidx >> 32);
-    c128* __restrict__ g = amp + base + off_t;
-    c128 v[PER];
-    if (init) {
-#pragma unroll
-      for (int i = 0; i < PER; ++i)
-        *reinterpret_cast<c128*>(reinterpret_cast<unsigned char*>(sm) + (sw_t ^ (swz_c((uint32_t)i * NT) << 4))) =
-            make_double2(0.0, 0.0);
-    } else if (!loaded) {
-      uint64_t hb[R];
-#pragma unroll
-      for (int k = 0; k < R; ++k) hb[k] = 1ull << byte_of(tb_lo, tb_hi, NTB + k);
-#pragma unroll
-      for (int i = 0; i < PER; ++i) {
-        uint64_t off = 0;
-#pragma unroll
-        for (int k = 0; k < R; ++k)
-          if ((i >> k) & 1) off |= hb[k];
-        cp_async16(reinterpret_cast<unsigned char*>(sm) + (sw_t ^ (swz_c((uint32_t)i * NT) << 4)), g + off);
-      }
-    }
-
-    tick(8);                      // issue: loads
-    // per-tile fixed-bit products of the fans, while the copies are in flight (one warp per fan)
+    // per-tile fixed-bit products of the fans, while the tile is still in flight (one warp per fan)
     for (int f = (int)warp; f < n_fans; f += (NT >> 5)) {
       const uint32_t off = (uint32_t)S.fanw[f] - dir_off;
       const uint64_t rec = S.fanw[off];
@@ -466,51 +499,46 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
       }
       if (lane == 0) fixp[f] = cmul(p, w[0]);
     }
-    tick(0);                      // fan products
-    if (!init) cp_async_wait_all();
-    __syncthreads();              // tile (or fan products) ready; also: every warp has left the previous tile
-    if (init && tile == init_tile) {
-      if (tid == 0) sm[swz(init_local)] = make_double2(1.0, 0.0);
-      __syncthreads();
+    // the previous tile's store has had the time of the fan products to read its buffer: wait for it and request the
+    // tile that uses the buffer next (for the other group)
+    if (warp == 0 && store_pending) {
+      bulk_wait_read();
+      __syncwarp();
+      if (!init) request(j_prev + kStages);
+      store_pending = false;
     }
-    tick(1);                      // wait for the tile + barrier
+    // (this barrier also keeps the threads of a group within one tile of each other: a parity wait cannot tell phase
+    // u from u + 2)
+    group_sync<NT>(g);
+    unsigned char* const smb = reinterpret_cast<unsigned char*>(S.stage[s]);
+    if (init) {
+#pragma unroll
+      for (int i = 0; i < PER; ++i) *reinterpret_cast<c128*>(smb + ((t + (uint32_t)i * NT) << 4)) = make_double2(0.0, 0.0);
+      if (tile == init_tile) {
+        group_sync<NT>(g);
+        if (t == 0) S.stage[s][swz(init_local)] = make_double2(1.0, 0.0);
+      }
+      group_sync<NT>(g);
+    } else {
+      mbar_wait(&S.full[s][u & 1u], (u >> 1) & 1u);
+    }
 
+    c128 v[PER];
     for (int rd = 0; rd < n_rounds; ++rd) {
       const uint4 hq = *reinterpret_cast<const uint4*>(&S.rh[rd]);
       const int ng = (int)(hq.x & 0xFFFFu), first = (int)(hq.x >> 16);
       const uint32_t srb[5] = {(hq.y & 0xFFFFu) << 4, (hq.y >> 16) << 4, (hq.z & 0xFFFFu) << 4, (hq.z >> 16) << 4, 0u};
-      const uint32_t my = S.thr[rd][tid];
-      const uint32_t lt = my & 0xFFFFu, stb = (my >> 16) << 4;
-      unsigned char* const smb = reinterpret_cast<unsigned char*>(sm);
+      const uint32_t lt = S.thr[rd][t], stb = swz(lt) << 4;
 
       // Gray-code walk over the 2^R register amplitudes: one XOR per shared-memory address
       {
-        uint32_t s = stb;
+        uint32_t so = stb;
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
-          if (i) s ^= srb[ctz_c(i)];
-          v[i ^ (i >> 1)] = *reinterpret_cast<const c128*>(smb + s);
+          if (i) so ^= srb[ctz_c(i)];
+          v[i ^ (i >> 1)] = *reinterpret_cast<const c128*>(smb + so);
         }
       }
-      if (overlap && rd == n_rounds - 1) {
-        __syncthreads();          // every warp holds its amplitudes: the shared-memory tile is free
-        loaded = tile + gridDim.x < n_tiles;
-        if (loaded) {
-          const c128* __restrict__ gn = amp + spread_tile(tile + gridDim.x) + off_t;
-          uint64_t hb[R];
-#pragma unroll
-          for (int k = 0; k < R; ++k) hb[k] = 1ull << byte_of(tb_lo, tb_hi, NTB + k);
-#pragma unroll
-          for (int i = 0; i < PER; ++i) {
-            uint64_t off = 0;
-#pragma unroll
-            for (int k = 0; k < R; ++k)
-              if ((i >> k) & 1) off |= hb[k];
-            cp_async16(reinterpret_cast<unsigned char*>(sm) + (sw_t ^ (swz_c((uint32_t)i * NT) << 4)), gn + off);
-          }
-        }
-      }
-      tick(2);                    // round: registers <- shared memory
       // the next record is fetched while the current one runs
       uint4 q = S.rec[first];
       for (int gi = first; gi < first + ng; ++gi) {
@@ -520,8 +548,8 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
         const bool active = ((fx_lo & q.w) == q.w) && ((fx_hi & fmh) == fmh) && ((lt & lm) == lm);
         if (active) {
           const uint32_t key1 = q.x & 0xFFu, key2 = (q.x >> 8) & 0xFFu;
-          const double* __restrict__ pay_t = S.pay + 2 * (q.z & 0xFFFFu);
-          const double* __restrict__ pay_d = S.pay + 2 * (q.z >> 16);
+          const double* __restrict__ pay_t = reinterpret_cast<const double*>(pay_b + ((q.z & 0xFFFFu) << 4));
+          const double* __restrict__ pay_d = reinterpret_cast<const double*>(pay_b + ((q.z >> 16) << 4));
           if (key1 == kKeyLayer) layer_apply<R>(v, pay_t, rm);       // (rm: which register bits carry a gate)
           else if (FULL && key1 != 0u) run_target<R>(v, key1, rm, pay_t);
           if (key2 == kKeyTab) {
@@ -549,101 +577,137 @@ k_tile(c128* __restrict__ amp, uint64_t n_tiles, uint64_t index_offset, const ui
         }
         q = nq;
       }
-
-      tick(3);                    // round: gates
-      if (direct_out && rd == n_rounds - 1) {
-        c128* __restrict__ go = amp + base + S.gthr[tid];
-        uint64_t hb[R];
-#pragma unroll
-        for (int k = 0; k < R; ++k) hb[k] = S.ghb[k];
-#pragma unroll
-        for (int rho = 0; rho < PER; ++rho) {
-          uint64_t off = 0;
-#pragma unroll
-          for (int k = 0; k < R; ++k)
-            if ((rho >> k) & 1) off |= hb[k];
-          __stcg(go + off, v[rho]);
-        }
-        tick(4);
-      } else {
-        uint32_t s = stb;
+      {
+        uint32_t so = stb;
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
-          if (i) s ^= srb[ctz_c(i)];
-          *reinterpret_cast<c128*>(smb + s) = v[i ^ (i >> 1)];
+          if (i) so ^= srb[ctz_c(i)];
+          *reinterpret_cast<c128*>(smb + so) = v[i ^ (i >> 1)];
         }
-        tick(4);                  // round: shared memory <- registers
-        __syncthreads();
       }
-      tick(5);                    // round: barrier
+      if (rd == n_rounds - 1) fence_async();      // the TMA store below reads what this thread just wrote
+      group_sync<NT>(g);
     }
-
-    if (!direct_out) {
-      uint64_t hb[R];
-#pragma unroll
-      for (int k = 0; k < R; ++k) hb[k] = 1ull << byte_of(tb_lo, tb_hi, NTB + k);
-#pragma unroll
-      for (int i = 0; i < PER; ++i) {
-        uint64_t off = 0;
-#pragma unroll
-        for (int k = 0; k < R; ++k)
-          if ((i >> k) & 1) off |= hb[k];
-        __stcs(g + off, *reinterpret_cast<const c128*>(reinterpret_cast<unsigned char*>(sm) + (sw_t ^ (swz_c((uint32_t)i * NT) << 4))));
+    // the finished tile leaves through the TMA unit (warp 0 of the group; lanes = sub-copies)
+    if (warp == 0) {
+      for (int sub = (int)lane; sub < n_sub; sub += 32) {
+        int c[5];
+        coords(fixedidx ^ index_offset, sub, c);
+        tma_store5(&tmap, S.stage[s] + (size_t)sub * tm.sub_amps, c);
       }
+      bulk_commit();
+      store_pending = true;
+      j_prev = j;
     }
-    tick(6);                      // stream the tile back
-    // the next tile's cp.async must not overwrite slots still being read (a direct first round writes shared
-    // memory only after the barrier at the head of the next tile)
-    if (!overlap) __syncthreads();
-    tick(7);                      // end-of-tile barrier
   }
+  if (warp == 0 && store_pending) bulk_wait_all();
 }
 
-template <int A, int R, int MINB, bool FULL>
-static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals, bool init, uint64_t init_tile,
-                  uint32_t init_local) {
+// ---- host side: the tile as a tensor box -------------------------------------------------------------------------
+// Field i of the tensor covers index bits [shift_i, shift_(i+1)): its low bits are tile bits (the box), the rest is
+// fixed per tile (the coordinate).  Field 0 is (re/im, index bits 0..2) = 16 doubles = one 128-byte swizzle line and
+// extends over the non-tile bits up to the next run.  Runs of tile bits longer than 8 are split (box dimensions are
+// limited to 256 elements).  More than 5 fields: the top runs are enumerated by separate copies, each of which lands
+// on a contiguous, 1 KB aligned part of the shared-memory tile.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+static int build_tile_map(b200_state* st, const int* tile, int a, TileMapDev& tm, CUtensorMap& map) {
+  const int n = st->n;
+  B200_REQUIRE(a >= 4 && tile[0] == 0 && tile[1] == 1 && tile[2] == 2, "TILE descriptor: index bits 0..2 must be tile bits");
+  int starts[16], lens[16], nch = 0;
+  for (int i = 3; i < a;) {
+    int j = i + 1;
+    while (j < a && tile[j] == tile[j - 1] + 1 && j - i < 8) ++j;
+    starts[nch] = tile[i];
+    lens[nch++] = j - i;
+    i = j;
+  }
+  const int keep = nch < 4 ? nch : 4;
+  tm = TileMapDev{};
+  for (int k = keep; k < nch; ++k)
+    for (int b = 0; b < lens[k]; ++b) {
+      B200_REQUIRE(tm.n_sub_bits < 9, "TILE descriptor: tile bits too scattered for the tensor map");
+      tm.sub_pos[tm.n_sub_bits++] = starts[k] + b;
+    }
+  cuuint64_t gdim[5], gstride[4];
+  cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+  int shift[6];
+  shift[0] = 0;
+  box[0] = 16;
+  for (int k = 0; k < keep; ++k) {
+    shift[1 + k] = starts[k];
+    box[1 + k] = 1u << lens[k];
+  }
+  const int rank = 1 + keep;
+  shift[rank] = n;
+  uint32_t box_doubles = 1;
+  for (int i = 0; i < 5; ++i) {
+    if (i < rank) {
+      tm.shift[i] = shift[i];
+      tm.width[i] = shift[i + 1] - shift[i];
+      // in doubles: field 0 also holds the re/im bit
+      gdim[i] = 1ull << (tm.width[i] + (i == 0 ? 1 : 0));
+      if (i > 0) gstride[i - 1] = 16ull << shift[i];
+    } else {
+      tm.shift[i] = 0;
+      tm.width[i] = 0;
+      gdim[i] = 1;
+      box[i] = 1;
+      gstride[i - 1] = 16ull << n;
+    }
+    box_doubles *= box[i];
+  }
+  tm.sub_amps = box_doubles / 2;
+  EncodeTiledFn enc = encode_tiled();
+  B200_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, st->amp, gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (%d) for a 2^%d tile on %d qubits", (int)r, a, n);
+    set_error(msg);
+    return 1;
+  }
+  return 0;
+}
+
+static_assert(sizeof(TileSmem<12>) <= 232448, "the 2^12 tile's shared memory exceeds the 227 KB a CTA can have");
+
+template <int A, bool FULL>
+static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals, const int* tile, bool init,
+                  uint64_t init_tile, uint32_t init_local) {
   constexpr int NT = 1 << (A - R);
-  const size_t smem = sizeof(TileSmem<A, R>);
+  const size_t smem = sizeof(TileSmem<A>);
   static bool configured[64] = {};
   if (!configured[st->device & 63]) {
-    B200_CUDA(cudaFuncSetAttribute(k_tile<A, R, MINB, false, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B200_CUDA(cudaFuncSetAttribute(k_tile<A, R, MINB, true, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(k_tile<A, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[st->device & 63] = true;
   }
+  TileMapDev tm;
+  CUtensorMap map;
+  if (build_tile_map(st, tile, A, tm, map)) return 1;
   const uint64_t n_tiles = st->dim >> A;
-  // persistent: exactly the resident CTAs, each walking tiles blockIdx, blockIdx + grid, ... (it requests its
-  // next tile while the last round of the current one still runs)
-  static const int ctas_env = getenv("B200_TILE_CTAS_PER_SM") ? atoi(getenv("B200_TILE_CTAS_PER_SM")) : 0;   // experiment
-  const uint64_t cap = (uint64_t)kSMs * (ctas_env > 0 && ctas_env < MINB ? ctas_env : MINB);
-  const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
-  static const bool timing = getenv("B200_TILE_TIMING") != nullptr;
-  unsigned long long* d_cyc = nullptr;
-  if (timing) {
-    B200_CUDA(cudaMalloc(&d_cyc, 9 * sizeof(unsigned long long)));
-    B200_CUDA(cudaMemsetAsync(d_cyc, 0, 9 * sizeof(unsigned long long), st->stream));
-  }
-  static const uint32_t flags = getenv("B200_TILE_NO_OVERLAP") ? 0u : 4u;     // (bit 0 was the L2 prefetch: removed)
-  if (timing)
-    k_tile<A, R, MINB, true, FULL><<<grid, NT, smem, st->stream>>>(st->amp, n_tiles, st->index_offset, d_desc, d_reals, d_cyc,
-                                                             flags | (init ? 2u : 0u), init_tile, init_local);
-  else
-    k_tile<A, R, MINB, false, FULL><<<grid, NT, smem, st->stream>>>(st->amp, n_tiles, st->index_offset, d_desc, d_reals,
-                                                              nullptr, flags | (init ? 2u : 0u), init_tile, init_local);
+  // persistent: one CTA per SM, each walking tiles blockIdx, blockIdx + grid, ...
+  const unsigned grid = (unsigned)(n_tiles < (uint64_t)kSMs ? n_tiles : (uint64_t)kSMs);
+  k_tile<A, FULL><<<grid, kGroups * NT, smem, st->stream>>>(map, tm, n_tiles, st->index_offset, d_desc, d_reals,
+                                                                  init ? 2u : 0u, init_tile, init_local);
   st->launches++;
   B200_CUDA(cudaGetLastError());
-  if (timing) {
-    unsigned long long h[9];
-    B200_CUDA(cudaMemcpyAsync(h, d_cyc, sizeof h, cudaMemcpyDeviceToHost, st->stream));
-    B200_CUDA(cudaStreamSynchronize(st->stream));
-    B200_CUDA(cudaFree(d_cyc));
-    double tot = 0;
-    for (int i = 0; i < 9; ++i) tot += (double)h[i];
-    fprintf(stderr, "[k_tile A=%d R=%d tiles=%llu ctas=%u] cycles per tile per CTA:", A, R, (unsigned long long)n_tiles, grid);
-    static const char* names[9] = {"fan_products", "wait", "rd_load", "rd_gates", "rd_store", "rd_barrier", "tile_store",
-                                   "end_barrier", "issue_loads"};
-    for (int i = 0; i < 9; ++i) fprintf(stderr, " %s=%.0f", names[i], (double)h[i] / (double)n_tiles);
-    fprintf(stderr, " total=%.0f\n", tot / (double)n_tiles);
-  }
   return 0;
 }
 
@@ -651,16 +715,16 @@ int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_d
                      const double* d_reals, size_t n_reals, uint64_t init_index) {
   B200_REQUIRE(wlen >= 5, "TILE descriptor too short");
   const uint64_t h0 = h_desc[0];
-  const int A = (int)(h0 & 0xFF), c = (int)((h0 >> 8) & 0xFF), R = (int)((h0 >> 16) & 0xFF);
+  const int A = (int)(h0 & 0xFF), c = (int)((h0 >> 8) & 0xFF), Rd = (int)((h0 >> 16) & 0xFF);
   const int n_rounds = (int)((h0 >> 24) & 0xFF), n_fans = (int)((h0 >> 32) & 0xFF);
   char msg[200];
-  if (A > st->n || c > A || (R != 4 && !(R == 3 && A == 11)) || n_fans > kMaxFans || n_rounds > kMaxRounds ||
-      st->n - A > 6 * kSpreadTabs) {
-    snprintf(msg, sizeof msg, "TILE descriptor not executable: A=%d c=%d R=%d fans=%d rounds=%d on %d qubits", A, c, R,
+  if (A > st->n || c > A || c < 3 || Rd != R || n_fans > kMaxFans || n_rounds > kMaxRounds || st->n - A > 6 * kSpreadTabs) {
+    snprintf(msg, sizeof msg, "TILE descriptor not executable: A=%d c=%d R=%d fans=%d rounds=%d on %d qubits", A, c, Rd,
              n_fans, n_rounds, st->n);
     set_error(msg);
     return 1;
   }
+  int tile[16];
   int prev = -1;
   for (int i = 0; i < A; ++i) {
     const int b = (int)(((i < 8 ? h_desc[1] : h_desc[2]) >> (8 * (i & 7))) & 0xFF);
@@ -668,7 +732,7 @@ int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_d
       set_error("TILE descriptor: tile bits must be ascending, below n_qubits, and 0..c-1 first");
       return 1;
     }
-    prev = b;
+    tile[i] = prev = b;
   }
   const uint64_t dir_off = h_desc[3] & 0xFFFFFFFFu, rounds_off = h_desc[3] >> 32;
   B200_REQUIRE(dir_off + (uint64_t)n_fans <= (uint64_t)wlen && rounds_off <= (uint64_t)wlen,
@@ -697,25 +761,22 @@ int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_d
   if (init && (init_index & ~(st->dim - 1)) == st->index_offset) {     // the 1 lives on this shard
     bool in_tile[64] = {};
     for (int i = 0; i < A; ++i) {
-      const int b = (int)(((i < 8 ? h_desc[1] : h_desc[2]) >> (8 * (i & 7))) & 0xFF);
-      in_tile[b] = true;
-      init_local |= (uint32_t)((init_index >> b) & 1ull) << i;
+      in_tile[tile[i]] = true;
+      init_local |= (uint32_t)((init_index >> tile[i]) & 1ull) << i;
     }
     init_tile = 0;
     for (int b = 0, k = 0; b < st->n; ++b)
       if (!in_tile[b]) init_tile |= ((init_index >> b) & 1ull) << k++;
   }
   switch (A) {
-    case 9:  return launch<9, 4, 8, true>(st, d_desc, d_reals, init, init_tile, init_local);
-    case 10: return launch<10, 4, 8, true>(st, d_desc, d_reals, init, init_tile, init_local);
-    case 11: return R == 3 ? launch<11, 3, 3, true>(st, d_desc, d_reals, init, init_tile, init_local)
-                           : launch<11, 4, 4, true>(st, d_desc, d_reals, init, init_tile, init_local);
+    case 9:  return launch<9, true>(st, d_desc, d_reals, tile, init, init_tile, init_local);
+    case 10: return launch<10, true>(st, d_desc, d_reals, tile, init, init_tile, init_local);
+    case 11: return launch<11, true>(st, d_desc, d_reals, tile, init, init_tile, init_local);
     // the production tile size also exists without the general target stages (see k_tile)
-    case 12: return full ? launch<12, 4, 2, true>(st, d_desc, d_reals, init, init_tile, init_local)
-                         : launch<12, 4, 2, false>(st, d_desc, d_reals, init, init_tile, init_local);
-    case 13: return launch<13, 4, 1, true>(st, d_desc, d_reals, init, init_tile, init_local);
+    case 12: return full ? launch<12, true>(st, d_desc, d_reals, tile, init, init_tile, init_local)
+                         : launch<12, false>(st, d_desc, d_reals, tile, init, init_tile, init_local);
     default:
-      snprintf(msg, sizeof msg, "TILE descriptor: tile size 2^%d is not built (9..13)", A);
+      snprintf(msg, sizeof msg, "TILE descriptor: tile size 2^%d is not built (9..12)", A);
       set_error(msg);
       return 1;
   }

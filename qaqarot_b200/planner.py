@@ -58,9 +58,11 @@ class PlanConfig:
     scan_limit: int = 4096    # how far ahead of the first unscheduled item a pass may look
     direct_io: bool = False   # flag the FIRST round as loadable straight from HBM (measured neutral at A = 12; the
                               # kernel accepts the flag and ignores it since its code was removed, csrc/tile.cu)
-    direct_out: bool = True   # let the LAST round store straight to HBM when its register bits avoid the row bits:
-                              # the kernel then requests the next tile while that round's gates run
-    kernel_tiles: Tuple[int, ...] = (9, 10, 11, 12, 13)   # tile sizes csrc/tile.cu instantiates (r = 4)
+    direct_out: bool = False  # flag the LAST round as storable straight to HBM (round 1; the TMA pipeline of round 2
+                              # stores every tile through the TMA unit and ignores the flag)
+    kernel_tiles: Tuple[int, ...] = (9, 10, 11, 12)       # tile sizes csrc/tile.cu instantiates (r = 4)
+    bank_pairs: bool = True   # keep both local bits of a shared-memory bank pair (0,3), (1,4), (2,5) out of one
+                              # round's register set when the gates can wait for the next round (see _thread_order)
     shears: bool = True       # 1-qubit gates as phase . rotation by three shears . phase (split_shears), and
                               # CX as H . CZ . H
 
@@ -686,6 +688,10 @@ def build_pass(remaining: List[Item], n: int, a: int, r: int, c: int, cfg: PlanC
                 new_r = t not in reg
                 if (new_t and len(tile) >= a) or (new_r and len(reg) >= r) or cost + _cost(it) > cfg.max_cost:
                     ok = False
+                elif new_r and cfg.bank_pairs and t < 6 and c >= 4 and (t + 3 if t < 3 else t - 3) in reg:
+                    # (index bits 0..5 are local bits 0..5 whenever bits 4 and 5 end up in the tile: a guess that only
+                    # costs bank conflicts when wrong)
+                    ok = False
                 else:
                     if new_t:
                         tile.add(t)
@@ -730,20 +736,24 @@ def build_pass(remaining: List[Item], n: int, a: int, r: int, c: int, cfg: PlanC
     return Pass(tl, rounds), [it for i, it in enumerate(remaining) if not done[i]]
 
 
+BANK_PAIRS = ((0, 3), (1, 4), (2, 5))
+
+
 def _thread_order(tile: List[int], reg: List[int]) -> List[int]:
-    """Local bit indices: register bits first, then thread bits.  The three lowest thread bits are chosen with
-    distinct residues mod 3 when possible, which makes the XOR-swizzled 16-byte shared-memory accesses of a
-    quarter warp conflict free (csrc/tile.cu)."""
+    """Local bit indices: register bits first, then thread bits.  The shared-memory slot of local index l is
+    l ^ ((l >> 3) & 7) (the TMA unit's 128-byte swizzle for 16-byte elements, csrc/tile.cu), so local bits 0 / 3,
+    1 / 4 and 2 / 5 each move an access by 1, 2 and 4 sixteen-byte bank groups and the others by none: the three
+    lowest thread bits (lane bits 0..2, the eight threads of a quarter warp) are taken one from each pair when the
+    register bits leave one, which makes the quarter warp's 16-byte accesses conflict free."""
     loc = {q: i for i, q in enumerate(tile)}
     regl = [loc[q] for q in reg]
     rest = [i for i in range(len(tile)) if i not in regl]
     first: List[int] = []
-    for res in (0, 1, 2):
-        for i in rest:
-            if i % 3 == res and i not in first:
+    for pair in BANK_PAIRS:
+        for i in pair:
+            if i in rest:
                 first.append(i)
                 break
-    first.sort()
     rest = first + [i for i in rest if i not in first]
     return regl + rest
 
