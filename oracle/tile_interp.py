@@ -76,7 +76,9 @@ def run_tile_pass(psi: np.ndarray, n: int, words: np.ndarray, reals: np.ndarray,
             roff_t, roff_d = roffs & 0xFFFFFFFF, roffs >> 32
             cond = ((fixed & fm) == fm) & ((local & lm) == lm)
             if tk == T_LAYER:
-                # up to one gate per register bit (reg mask says which), each as three shears; payload 4 x (z, x, y, 0)
+                # up to one rotation per register bit (reg mask says which), each as in-place shears
+                # a0 += z a1; a1 += x a0; a0 += y a1 (y = 0: two updates, the record's diagonal stage rescales);
+                # payload 4 x (z, x, y, 0)
                 assert int(fm) == 0 and int(lm) == 0 and 0 < (int(rm) & 15) < (1 << r)
                 assert dk in (D_NONE, D_FANT, D_FAN, D_W, D_FIX, D_TAB)
                 pay = cplx(roff_t, 8)
@@ -90,7 +92,8 @@ def run_tile_pass(psi: np.ndarray, n: int, words: np.ndarray, reals: np.ndarray,
                     a0, a1 = psi[i0], psi[i1]
                     a0 = a0 + z * a1
                     a1 = a1 + x * a0
-                    a0 = a0 + y * a1
+                    if y != 0.0:
+                        a0 = a0 + y * a1
                     psi[i0], psi[i1] = a0, a1
             elif tk != T_NONE:
                 assert j < r and dk in (D_NONE, D_FANT, D_FAN, D_W, D_FIX)

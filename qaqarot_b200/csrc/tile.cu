@@ -48,11 +48,14 @@
 //     A record runs where the fixed-bit mask (per tile) and the thread mask (per thread) are satisfied:
 //     target stage on register bit j:  1 = complex 2x2 (8 reals, row major re/im), 2 = real 2x2 (same layout),
 //                                      3 = pair swap; pairs whose other register bits satisfy reg_mask
-//                                      6 = layer: for each register bit k in reg_mask (bits 0..3) the three
-//                                          in-place shears a0 += z a1; a1 += x a0; a0 += y a1 on the pairs of bit
-//                                          k, payload 4 x (z, x, y, 0); j unused.  With z = y = -tan(t/2), x = sin t
-//                                          a rotation by t: the planner writes every 1-qubit unitary as
-//                                          phase . rotation . phase (planner.split_shears)
+//                                      6 = layer: for each register bit k in reg_mask (bits 0..3) the in-place
+//                                          shears a0 += z a1; a1 += x a0; a0 += y a1 (skipped when y = 0) on the
+//                                          pairs of bit k, payload 4 x (z, x, y, 0); j unused.  z = y = -tan(t/2),
+//                                          x = sin t: the rotation by t.  z = -tan t, x = sin t cos t, y = 0, |t| <=
+//                                          pi/4: the rotation by t up to cos t on every amplitude and 1 / cos^2 t
+//                                          on those with bit k set, which the planner multiplies into the diag
+//                                          stage of the same record (planner.shear_params); every 1-qubit unitary
+//                                          is phase . rotation . phase (planner.split_rotation)
 //     diag stage:  1 / 2 = fan  amp *= fix[fan] * lane_t[lane] * warp_t[warp] (* reg_t[rho] for kind 2) on the
 //                  amplitudes with register bit j set (j = R: all); tables 32 + 2^(A-R-5) (+ 2^R) complex
 //                  3 = phase  amp *= reals[offset] where rho satisfies reg_mask (never fused with a target stage)
@@ -245,22 +248,33 @@ __device__ __forceinline__ void fan_apply(c128 (&v)[1 << R], c128 wt, const doub
 //   key2 = 8 j + diag kind, j = 4 for "every amplitude"               (0: no diag stage)
 constexpr uint32_t kKeyLayer = 0xF0u, kKeyTab = 0xF1u;
 
-// (a0, a1) <- E(y) F(x) E(z) (a0, a1) on the pairs of register bit J, for the J in `mask`; payload 4 x (z, x, y, -)
+// (a0, a1) <- E(y) F(x) E(z) (a0, a1) on the pairs of register bit J, for the J in `mask`; payload 4 x (z, x, y, -).
+// y = 0 (two updates; the record's diag stage rescales) skips the third loop: a warp-uniform branch.
 template <int R>
 __device__ __forceinline__ void layer_apply(c128 (&v)[1 << R], const double* __restrict__ pay, uint32_t mask) {
 #pragma unroll
   for (int J = 0; J < R; ++J) {
     if (!((mask >> J) & 1u)) continue;
-    const double z = pay[4 * J], x = pay[4 * J + 1], y = pay[4 * J + 2];
+    const double2 zx = reinterpret_cast<const double2*>(pay)[2 * J];
+    const double y = pay[4 * J + 2];
 #pragma unroll
     for (int rho = 0; rho < (1 << R); ++rho) {
       if (rho & (1 << J)) continue;
       c128& a0 = v[rho];
       c128& a1 = v[rho | (1 << J)];
       asm("fma.rn.f64 %0, %4, %2, %0;\n\tfma.rn.f64 %1, %4, %3, %1;\n\t"
-          "fma.rn.f64 %2, %5, %0, %2;\n\tfma.rn.f64 %3, %5, %1, %3;\n\t"
-          "fma.rn.f64 %0, %6, %2, %0;\n\tfma.rn.f64 %1, %6, %3, %1;"
-          : "+d"(a0.x), "+d"(a0.y), "+d"(a1.x), "+d"(a1.y) : "d"(z), "d"(x), "d"(y));
+          "fma.rn.f64 %2, %5, %0, %2;\n\tfma.rn.f64 %3, %5, %1, %3;"
+          : "+d"(a0.x), "+d"(a0.y), "+d"(a1.x), "+d"(a1.y) : "d"(zx.x), "d"(zx.y));
+    }
+    if (y != 0.0) {
+#pragma unroll
+      for (int rho = 0; rho < (1 << R); ++rho) {
+        if (rho & (1 << J)) continue;
+        c128& a0 = v[rho];
+        c128& a1 = v[rho | (1 << J)];
+        asm("fma.rn.f64 %0, %4, %2, %0;\n\tfma.rn.f64 %1, %4, %3, %1;"
+            : "+d"(a0.x), "+d"(a0.y) : "d"(a1.x), "d"(a1.y), "d"(y));
+      }
     }
   }
 }
@@ -325,9 +339,14 @@ constexpr int R = 4;               // register bits per round (2^R amplitudes pe
 
 constexpr int kMaxPayload = 2560;  // float64 payload of one pass kept in shared memory (planner.MAX_PAYLOAD)
 constexpr int kMaxFanWords = 512;  // fan directory + records of the pass's fans (planner keeps a pass below this)
-// record (one uint4): x = key1 | key2<<8 | fan<<16 | fixed mask bits 32..39<<24
-//                     y = thread mask | reg mask<<16    z = target payload | diag payload<<16 (complex units, relative)
-//                     w = fixed mask bits 0..31
+// record (one uint4), three shapes told apart by x & 3 -- the two that carry a layered circuit or a QFT are decoded
+// with a handful of instructions, everything else takes the general path:
+//   1  LT   rotations + table          x = 1 | rotation mask<<2 | has table<<8      z = selectors p1 | p2<<8 | p3<<16
+//   2  LF   rotations + fan            x = 2 | rotation mask<<2 | j<<6 (4: every amplitude) | diag kind<<9 | fan<<12
+//   0  general (conditions, 2x2, pair swap, phase)
+//                                      x = key1<<2 | key2<<10 | fan<<18 | fixed mask bits 32..39<<24
+//                                      z = thread mask | reg mask<<16                w = fixed mask bits 0..31
+//   all: y = target payload | diag payload<<16 (complex units, relative to the pass's payload)
 
 struct RoundHdr {                  // 16 bytes
   uint16_t n_gates, first;         // records [first, first + n_gates)
@@ -362,17 +381,18 @@ struct TileSmem {
 // FULL = false leaves out the general target stages (complex / real 2x2, pair swap, their controlled forms): a pass
 // of 1-qubit unitaries and phases needs none of them, and the kernel without their 24 unrolled bodies runs every
 // record faster (round 1: 45.2 -> 41.0 ms on the 30-qubit QFT).
-template <int A, bool FULL>
+template <int A, bool FULL, bool TIMING>
 __global__ void __launch_bounds__(kGroups * (1 << (A - R)), 1)
 k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMapDev tm, uint64_t n_tiles,
        uint64_t index_offset, const uint64_t* __restrict__ desc, const double* __restrict__ reals, uint32_t flags,
-       uint64_t init_tile, uint32_t init_local) {
+       uint64_t init_tile, uint32_t init_local, unsigned long long* __restrict__ phase_cycles) {
   constexpr int NT = 1 << (A - R), PER = 1 << R, NTB = A - R;
   constexpr int NWARP_T = (NTB > 5) ? (1 << (NTB - 5)) : 1;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   TileSmem<A>& S = *reinterpret_cast<TileSmem<A>*>(smem_raw);
 
-  const uint32_t tid = threadIdx.x;
+  uint32_t tid;                    // (volatile: ptxas otherwise re-reads SR_TID.X inside the record loop)
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
   const uint64_t h0 = desc[0], tb_lo = desc[1], tb_hi = desc[2];
   const int n_rounds = (int)((h0 >> 24) & 0xFF), n_fans = (int)((h0 >> 32) & 0xFF);
   const uint32_t dir_off = (uint32_t)(desc[3] & 0xFFFFFFFFu), rounds_off = (uint32_t)(desc[3] >> 32);
@@ -425,10 +445,24 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
       const uint32_t pt = tk == T_NONE || tk == T_X ? 0u : (((uint32_t)roffs - pay_lo) >> 1);
       const uint32_t pd = dk == D_NONE ? 0u : (((uint32_t)(roffs >> 32) - pay_lo) >> 1);
       const uint32_t jj = j < (uint32_t)R ? j : 4u;            // 4 = no register target ("every amplitude")
-      const uint32_t key1 = tk == T_NONE ? 0u : tk == T_LAYER ? kKeyLayer : 16u * jj + tk + (rm != 0 ? 8u : 0u);
-      const uint32_t key2 = dk == D_NONE ? 0u : dk == D_TAB ? kKeyTab : 8u * jj + dk;
-      S.rec[first + gi] = make_uint4(key1 | (key2 << 8) | (fan << 16) | ((uint32_t)(fm >> 32) << 24),
-                                     lm | (rm << 16), pt | (pd << 16), (uint32_t)fm);
+      const bool plain = lm == 0 && fm == 0 && (tk == T_NONE || tk == T_LAYER);
+      uint4 rec;
+      rec.y = pt | (pd << 16);
+      if (plain && (dk == D_NONE || dk == D_TAB)) {
+        rec.x = 1u | ((tk == T_LAYER ? rm & 15u : 0u) << 2) | (dk == D_TAB ? 0x100u : 0u);
+        rec.z = ((rm >> 4) & 63u) | (((rm >> 10) & 63u) << 8) | ((fan & 63u) << 16);
+        rec.w = 0;
+      } else if (plain && (dk == D_FANT || dk == D_FAN || dk == D_W || dk == D_FIX)) {
+        rec.x = 2u | ((tk == T_LAYER ? rm & 15u : 0u) << 2) | (jj << 6) | (dk << 9) | ((fan & 63u) << 12);
+        rec.z = rec.w = 0;
+      } else {
+        const uint32_t key1 = tk == T_NONE ? 0u : tk == T_LAYER ? kKeyLayer : 16u * jj + tk + (rm != 0 ? 8u : 0u);
+        const uint32_t key2 = dk == D_NONE ? 0u : dk == D_TAB ? kKeyTab : 8u * jj + dk;
+        rec.x = (key1 << 2) | (key2 << 10) | ((fan & 63u) << 18) | ((uint32_t)(fm >> 32) << 24);
+        rec.z = lm | (rm << 16);
+        rec.w = (uint32_t)fm;
+      }
+      S.rec[first + gi] = rec;
     }
   }
   __syncthreads();
@@ -450,6 +484,7 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
 
   // ---- compute groups ----------------------------------------------------------------------------------------
   const uint32_t g = tid / NT, t = tid % NT, lane = t & 31u, warp = t >> 5;
+  const uint32_t lane_off = lane << 4, warp_off = (32u + (NWARP_T > 1 ? warp : 0u)) << 4;      // into a fan's tables
   c128* const fixp = S.fix[g];
   unsigned char* const pay_b = reinterpret_cast<unsigned char*>(S.pay);
   // request tile j of this CTA into its buffer (warp 0 of a group; lanes = sub-copies)
@@ -472,6 +507,15 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
   }
   bool store_pending = false;       // warp 0: the previous tile's store has not been waited for yet
   uint32_t j_prev = 0;
+  // B200_TILE_TIMING=1: thread 0 of every group accumulates the cycles it spends in each phase of a tile
+  long long tk0 = TIMING ? clock64() : 0;
+  auto tick = [&](int phase) {
+    if (TIMING && t == 0) {
+      const long long now = clock64();
+      atomicAdd(phase_cycles + phase, (unsigned long long)(now - tk0));
+      tk0 = now;
+    }
+  };
   for (uint32_t j = g;; j += kGroups) {
     const uint64_t tile = blockIdx.x + (uint64_t)j * gridDim.x;
     if (tile >= n_tiles) break;
@@ -499,6 +543,7 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
       }
       if (lane == 0) fixp[f] = cmul(p, w[0]);
     }
+    tick(0);                        // fan products
     // the previous tile's store has had the time of the fan products to read its buffer: wait for it and request the
     // tile that uses the buffer next (for the other group)
     if (warp == 0 && store_pending) {
@@ -507,9 +552,11 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
       if (!init) request(j_prev + kStages);
       store_pending = false;
     }
+    tick(1);                        // wait for the previous store's reads + request the next tile
     // (this barrier also keeps the threads of a group within one tile of each other: a parity wait cannot tell phase
     // u from u + 2)
     group_sync<NT>(g);
+    tick(2);                        // group barrier
     unsigned char* const smb = reinterpret_cast<unsigned char*>(S.stage[s]);
     if (init) {
 #pragma unroll
@@ -522,6 +569,7 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
     } else {
       mbar_wait(&S.full[s][u & 1u], (u >> 1) & 1u);
     }
+    tick(3);                        // wait for the tile
 
     c128 v[PER];
     for (int rd = 0; rd < n_rounds; ++rd) {
@@ -539,44 +587,90 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
           v[i ^ (i >> 1)] = *reinterpret_cast<const c128*>(smb + so);
         }
       }
+      tick(4);                      // round: registers <- shared memory (issue)
       // the next record is fetched while the current one runs
       uint4 q = S.rec[first];
       for (int gi = first; gi < first + ng; ++gi) {
         const uint4 nq = S.rec[gi + 1];
-        const uint32_t lm = q.y & 0xFFFFu, rm = q.y >> 16, fmh = q.x >> 24;
-        // fixed-bit condition: CTA-uniform; thread-bit condition: per thread
-        const bool active = ((fx_lo & q.w) == q.w) && ((fx_hi & fmh) == fmh) && ((lt & lm) == lm);
-        if (active) {
-          const uint32_t key1 = q.x & 0xFFu, key2 = (q.x >> 8) & 0xFFu;
-          const double* __restrict__ pay_t = reinterpret_cast<const double*>(pay_b + ((q.z & 0xFFFFu) << 4));
-          const double* __restrict__ pay_d = reinterpret_cast<const double*>(pay_b + ((q.z >> 16) << 4));
-          if (key1 == kKeyLayer) layer_apply<R>(v, pay_t, rm);       // (rm: which register bits carry a gate)
-          else if (FULL && key1 != 0u) run_target<R>(v, key1, rm, pay_t);
-          if (key2 == kKeyTab) {
-            // one table per combination of (up to) three selector bits: index bits outside the tile (CTA-uniform per
-            // tile) or thread bits of the tile (48 + local position); 63 = none, which reads as 0
-            const uint32_t p1 = (rm >> 4) & 63u, p2 = (rm >> 10) & 63u, p3 = (q.x >> 16) & 63u;
-            const uint64_t sel = fixedidx | ((uint64_t)lt << 48);
-            const uint32_t var = (uint32_t)((sel >> p1) & 1ull) | ((uint32_t)((sel >> p2) & 1ull) << 1) |
-                                 ((uint32_t)((sel >> p3) & 1ull) << 2);
-            const uint32_t m = (p1 != 63u) + (p2 != 63u) + (p3 != 63u);
-            tab_apply<R>(v, reinterpret_cast<const double2*>(pay_d) + var, 1u << m);
-          } else if (key2 != 0u) {
-            const uint32_t dk = key2 & 7u;
-            c128 wt = make_double2(1.0, 0.0);
-            if (dk == D_FANT || dk == D_FAN) {
-              const double2* __restrict__ tab = reinterpret_cast<const double2*>(pay_d);
-              wt = cmul(fixp[(q.x >> 16) & 0xFFu], cmul(tab[lane], tab[32 + (NWARP_T > 1 ? warp : 0)]));
-            } else if (dk == D_FIX) {
-              wt = fixp[(q.x >> 16) & 0xFFu];
-            } else if (dk == D_W) {
-              wt = *reinterpret_cast<const double2*>(pay_d);             // the factor itself
+        const uint32_t op = q.x & 3u;
+        const double* __restrict__ pay_t = reinterpret_cast<const double*>(pay_b + ((q.y & 0xFFFFu) << 4));
+        const double* __restrict__ pay_d = reinterpret_cast<const double*>(pay_b + ((q.y >> 16) << 4));
+        if (op != 0u) {
+          const uint32_t rot = (q.x >> 2) & 15u;
+          if (rot) layer_apply<R>(v, pay_t, rot);
+          if (op == 1u) {
+            if (q.x & 0x100u) {
+              // one table per combination of (up to) three selector bits: index bits outside the tile (CTA-uniform per
+              // tile) or thread bits of the tile (48 + local position); 63 = none, which reads as 0
+              uint32_t var = 0, stride = 1;
+              if (q.z != 0x3F3F3Fu) {
+                const uint32_t p1 = q.z & 63u, p2 = (q.z >> 8) & 63u, p3 = (q.z >> 16) & 63u;
+                const uint64_t sel = fixedidx | ((uint64_t)lt << 48);
+                var = (uint32_t)((sel >> p1) & 1ull) | ((uint32_t)((sel >> p2) & 1ull) << 1) |
+                      ((uint32_t)((sel >> p3) & 1ull) << 2);
+                stride = 1u << ((p1 != 63u) + (p2 != 63u) + (p3 != 63u));
+              }
+              tab_apply<R>(v, reinterpret_cast<const double2*>(pay_d) + var, stride);
             }
-            run_diag<R, NWARP_T>(v, key2, rm, pay_d, wt);
+          } else {
+            const uint32_t dk = (q.x >> 9) & 7u, fan = (q.x >> 12) & 63u;
+            c128 wt;
+            if (dk == D_W) {
+              wt = *reinterpret_cast<const double2*>(pay_d);             // the factor itself
+            } else {
+              wt = fixp[fan];
+              if (dk != D_FIX) {
+                const unsigned char* tb = reinterpret_cast<const unsigned char*>(pay_d);
+                wt = cmul(wt, cmul(*reinterpret_cast<const double2*>(tb + lane_off),
+                                   *reinterpret_cast<const double2*>(tb + warp_off)));
+              }
+            }
+            const double2* __restrict__ reg_t = reinterpret_cast<const double2*>(pay_d) + 32 + NWARP_T;
+            switch ((q.x >> 6) & 7u) {
+#define B200_F_CASE(J)                                              \
+              case J:                                               \
+                if (dk == D_FAN) fan_apply<R, J>(v, wt, reg_t);     \
+                else fant_apply<R, J>(v, wt);                       \
+                break;
+              B200_F_CASE(0) B200_F_CASE(1) B200_F_CASE(2) B200_F_CASE(3) B200_F_CASE(4)
+#undef B200_F_CASE
+              default: break;
+            }
+          }
+        } else {
+          const uint32_t lm = q.z & 0xFFFFu, rm = q.z >> 16, fmh = q.x >> 24;
+          // fixed-bit condition: CTA-uniform; thread-bit condition: per thread
+          const bool active = ((fx_lo & q.w) == q.w) && ((fx_hi & fmh) == fmh) && ((lt & lm) == lm);
+          if (active) {
+            const uint32_t key1 = (q.x >> 2) & 0xFFu, key2 = (q.x >> 10) & 0xFFu, fan = (q.x >> 18) & 63u;
+            if (key1 == kKeyLayer) layer_apply<R>(v, pay_t, rm & 15u);
+            else if (FULL && key1 != 0u) run_target<R>(v, key1, rm, pay_t);
+            if (key2 == kKeyTab) {
+              const uint32_t p1 = (rm >> 4) & 63u, p2 = (rm >> 10) & 63u, p3 = fan;
+              const uint64_t sel = fixedidx | ((uint64_t)lt << 48);
+              const uint32_t var = (uint32_t)((sel >> p1) & 1ull) | ((uint32_t)((sel >> p2) & 1ull) << 1) |
+                                   ((uint32_t)((sel >> p3) & 1ull) << 2);
+              const uint32_t m = (p1 != 63u) + (p2 != 63u) + (p3 != 63u);
+              tab_apply<R>(v, reinterpret_cast<const double2*>(pay_d) + var, 1u << m);
+            } else if (key2 != 0u) {
+              const uint32_t dk = key2 & 7u;
+              c128 wt = make_double2(1.0, 0.0);
+              if (dk == D_FANT || dk == D_FAN) {
+                const unsigned char* tb = reinterpret_cast<const unsigned char*>(pay_d);
+                wt = cmul(fixp[fan], cmul(*reinterpret_cast<const double2*>(tb + lane_off),
+                                          *reinterpret_cast<const double2*>(tb + warp_off)));
+              } else if (dk == D_FIX) {
+                wt = fixp[fan];
+              } else if (dk == D_W) {
+                wt = *reinterpret_cast<const double2*>(pay_d);           // the factor itself
+              }
+              run_diag<R, NWARP_T>(v, key2, rm, pay_d, wt);
+            }
           }
         }
         q = nq;
       }
+      tick(5);                      // round: gates
       {
         uint32_t so = stb;
 #pragma unroll
@@ -586,7 +680,9 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
         }
       }
       if (rd == n_rounds - 1) fence_async();      // the TMA store below reads what this thread just wrote
+      tick(6);                      // round: shared memory <- registers
       group_sync<NT>(g);
+      tick(7);                      // round: barrier
     }
     // the finished tile leaves through the TMA unit (warp 0 of the group; lanes = sub-copies)
     if (warp == 0) {
@@ -599,6 +695,7 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
       store_pending = true;
       j_prev = j;
     }
+    tick(8);                        // issue the store
   }
   if (warp == 0 && store_pending) bulk_wait_all();
 }
@@ -695,7 +792,8 @@ static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals,
   const size_t smem = sizeof(TileSmem<A>);
   static bool configured[64] = {};
   if (!configured[st->device & 63]) {
-    B200_CUDA(cudaFuncSetAttribute(k_tile<A, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(k_tile<A, FULL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(k_tile<A, FULL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[st->device & 63] = true;
   }
   TileMapDev tm;
@@ -704,10 +802,34 @@ static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals,
   const uint64_t n_tiles = st->dim >> A;
   // persistent: one CTA per SM, each walking tiles blockIdx, blockIdx + grid, ...
   const unsigned grid = (unsigned)(n_tiles < (uint64_t)kSMs ? n_tiles : (uint64_t)kSMs);
-  k_tile<A, FULL><<<grid, kGroups * NT, smem, st->stream>>>(map, tm, n_tiles, st->index_offset, d_desc, d_reals,
-                                                                  init ? 2u : 0u, init_tile, init_local);
+  static const bool timing = getenv("B200_TILE_TIMING") != nullptr;
+  if (!timing) {
+    k_tile<A, FULL, false><<<grid, kGroups * NT, smem, st->stream>>>(map, tm, n_tiles, st->index_offset, d_desc, d_reals,
+                                                                     init ? 2u : 0u, init_tile, init_local, nullptr);
+    st->launches++;
+    B200_CUDA(cudaGetLastError());
+    return 0;
+  }
+  constexpr int kPhases = 9;
+  unsigned long long* d_cyc = nullptr;
+  B200_CUDA(cudaMalloc(&d_cyc, kPhases * sizeof(unsigned long long)));
+  B200_CUDA(cudaMemsetAsync(d_cyc, 0, kPhases * sizeof(unsigned long long), st->stream));
+  k_tile<A, FULL, true><<<grid, kGroups * NT, smem, st->stream>>>(map, tm, n_tiles, st->index_offset, d_desc, d_reals,
+                                                                  init ? 2u : 0u, init_tile, init_local, d_cyc);
   st->launches++;
   B200_CUDA(cudaGetLastError());
+  unsigned long long h[kPhases];
+  B200_CUDA(cudaMemcpyAsync(h, d_cyc, sizeof h, cudaMemcpyDeviceToHost, st->stream));
+  B200_CUDA(cudaStreamSynchronize(st->stream));
+  B200_CUDA(cudaFree(d_cyc));
+  double tot = 0;
+  for (int i = 0; i < kPhases; ++i) tot += (double)h[i];
+  fprintf(stderr, "[k_tile A=%d tiles=%llu ctas=%u copies/tile=%d] cycles per tile per group:", A, (unsigned long long)n_tiles,
+          grid, 1 << tm.n_sub_bits);
+  static const char* names[kPhases] = {"fan_products", "store_wait+request", "group_barrier", "wait_tile", "rd_load",
+                                       "rd_gates", "rd_store", "rd_barrier", "store_issue"};
+  for (int i = 0; i < kPhases; ++i) fprintf(stderr, " %s=%.0f", names[i], (double)h[i] / (double)n_tiles);
+  fprintf(stderr, " total=%.0f\n", tot / (double)n_tiles);
   return 0;
 }
 

@@ -85,7 +85,7 @@ class Item:
         self.aux = aux              # swap: second qubit
         self.n_prims = n_prims
         self.pos = -1
-        self.sh = None              # mat: (z, x, y) when m = shear_matrix(z, x, y) is applied as three shears
+        self.sh = None              # mat: theta when m = rotation_matrix(theta) runs as in-place shears of a LAYER record
         self.refresh()
 
     def refresh(self):
@@ -146,24 +146,53 @@ def _unit(z: complex) -> complex:
     return z / abs(z)
 
 
-def shear_matrix(z: float, x: float, y: float) -> np.ndarray:
-    """The real 2x2 (row major) that the three in-place shears of a LAYER record apply to a pair (a0, a1)
-    (csrc/tile.cu):  a0 += z a1;  a1 += x a0;  a0 += y a1."""
-    return np.array([1.0 + x * y, z + y * (1.0 + x * z), x, 1.0 + x * z], dtype=complex)
+def rotation_matrix(theta: float) -> np.ndarray:
+    """R(theta) = [[cos, -sin], [sin, cos]], row major."""
+    c, sn = math.cos(theta), math.sin(theta)
+    return np.array([c, -sn, sn, c], dtype=complex)
 
 
-def split_shears(m) -> Optional[Tuple[complex, complex, float, float, float, complex]]:
+def shear_params(theta: float, exact: bool = False) -> Tuple[float, float, float, float, float]:
+    """(z, x, y, c_all, c_bit): R(theta), |theta| <= pi/2, as the in-place updates of a LAYER record (csrc/tile.cu)
+
+        a0 += z a1;   a1 += x a0;   a0 += y a1   (skipped when y = 0)
+
+    followed by a factor c_all on both amplitudes and c_bit on a1, which the record's diagonal stage applies.
+    |theta| <= pi/4: two updates, z = -t, x = t / (1 + t^2) with t = tan(theta), leaving (b0 / c, b1 c) with
+    c = cos(theta): c_all = c, c_bit = 1 + t^2, both within [1/2, 2].  Larger angles, or `exact`: the three shears of
+    the lifting scheme, z = y = -tan(theta / 2), x = sin(theta), c_all = c_bit = 1 at the price of the third update
+    (cheaper than two updates and a table when the record has no other use for a table)."""
+    if not exact and abs(theta) <= math.pi / 4 + 1e-15:
+        t = math.tan(theta)
+        return -t, t / (1.0 + t * t), 0.0, 1.0 / math.sqrt(1.0 + t * t), 1.0 + t * t
+    z = -math.tan(theta / 2.0)
+    return z, math.sin(theta), z, 1.0, 1.0
+
+
+def shear_item(q: int, theta: float) -> "Item":
+    """The rotation by theta, |theta| <= pi/2, on index bit q as the planner schedules it: a `mat` item flagged to run
+    as the in-place updates of a LAYER record."""
+    it = Item("mat", t=q, m=rotation_matrix(theta))
+    it.sh = float(theta)
+    return it
+
+
+_ANTI = np.array([0, -1, 1, 0], dtype=complex)        # R(pi / 2)
+
+
+def split_rotation(m, allow_anti: bool = True) -> Optional[Tuple[complex, complex, float, complex, bool]]:
     """A 2x2 unitary as
 
-        m = g * diag(1, dl) . R(theta) . diag(1, dr),     |g| = |dl| = |dr| = 1,  |theta| <= pi/2,
+        m = g * diag(1, dl) . A^anti . R(theta) . diag(1, dr),   |g| = |dl| = |dr| = 1,
 
-    with the rotation R(theta) = [[cos, -sin], [sin, cos]] applied as three shears (the lifting scheme)
-    z = y = -tan(theta / 2), x = sin(theta): 3 FMAs per component of an amplitude pair, in place, no temporaries --
-    against 8 multiply-adds and a copy for a complex 2x2.  `dr` joins the phases in front of the gate, `g` the
-    segment's global factor, and `dl` stays on the wire as a pending phase (it commutes with every control and
-    phase and is absorbed by the next gate on the wire).  A real rotation keeps dl = dr = 1; a real reflection
-    (H) is a rotation times Z, dl = -1.
-    Returns (g, dl, z, x, y, dr), or None when the pieces do not reproduce `m` to rounding (not unitary)."""
+    with R(theta) = [[cos, -sin], [sin, cos]] and A = R(pi / 2) = [[0, -1], [1, 0]]; |theta| <= pi/4 when `allow_anti`,
+    else |theta| <= pi/2 and anti = False.  R(theta) runs in place on the register tile (shear_params: two FMAs per
+    component of an amplitude pair for |theta| <= pi/4, three beyond, against 8 multiply-adds and a copy for a complex
+    2x2).  `dr` joins the phases in front of the gate, `g` the segment's global factor, and diag(1, dl) . A^anti stays
+    on the wire as a pending diagonal or anti-diagonal factor: every control and phase commutes with it or is
+    conjugated by it (emit_conjugated), and the next gate on the wire absorbs it.  A real rotation keeps dl = dr = 1; a
+    real reflection (H) is a rotation times Z.
+    Returns (g, dl, theta, dr, anti), or None when the pieces do not reproduce `m` to rounding (not unitary)."""
     a, b, c, d = (complex(v) for v in np.asarray(m).reshape(4))          # (plain Python arithmetic: this runs once
     if not all(math.isfinite(v.real) and math.isfinite(v.imag) for v in (a, b, c, d)):     # per gate of a circuit)
         return None
@@ -183,12 +212,18 @@ def split_shears(m) -> Optional[Tuple[complex, complex, float, float, float, com
         dr = -_unit(b) / g
         # the phases are read off the LARGE entries (those of small ones are only known to ~eps / |entry|)
         dl = _unit(d) / (g * dr) if abs(a) >= abs(c) else _unit(c) / g
-    z, x = -math.tan(theta / 2.0), math.sin(theta)
-    s00, s01, s10, s11 = 1.0 + x * z, z + z * (1.0 + x * z), x, 1.0 + x * z          # shear_matrix(z, x, z)
-    err = max(abs(g * s00 - a), abs(g * s01 * dr - b), abs(g * dl * s10 - c), abs(g * dl * s11 * dr - d))
-    if not err <= 2e-15:
+    anti = allow_anti and abs(theta) > math.pi / 4 + 1e-15
+    if anti:                                       # R(theta) = +-A . R(theta -+ pi/2)
+        if theta < 0:
+            g = -g
+        theta -= math.copysign(math.pi / 2, theta)
+    r00, r01, r10, r11 = (v.real for v in rotation_matrix(theta))
+    if anti:
+        r00, r01, r10, r11 = -r10, -r11, r00, r01
+    err = max(abs(g * r00 - a), abs(g * r01 * dr - b), abs(g * dl * r10 - c), abs(g * dl * r11 * dr - d))
+    if not err <= 3e-15:
         return None
-    return g, dl, float(z), float(x), float(z), dr
+    return g, dl, float(theta), dr, anti
 
 
 def fold_conjugated_phases(prims: Sequence[Prim]) -> List[Prim]:
@@ -401,24 +436,48 @@ def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = 
             else:
                 emit_phase((q,), m[3], cnt, early=True)
             return
-        if np.array_equal(m, _XM):
+        if _is_antidiag(m):
+            if shears:
+                # [[0, a], [b, 0]] = diag(-a, b) . R(pi / 2): a rotation like any other (three in-place shears) instead
+                # of a pair swap, which only the kernel built with the general target stages executes
+                it = shear_item(q, math.pi / 2)
+                it.n_prims = cnt
+                push(it, last_touch[q])
+                scalar[0] *= -m[1]
+                emit_phase((q,), -m[2] / m[1], 0, early=True)
+                return
+            # [[0, a], [b, 0]] = diag(a, b) . X
             push(Item("x", t=q, n_prims=cnt), last_touch[q])
+            if m[1] != 1.0:
+                scalar[0] *= m[1]
+            emit_phase((q,), m[2] / m[1], 0, early=True)
             return
-        sp = split_shears(m) if shears else None
+        sp = split_rotation(m, allow_anti=keep_diag) if shears else None
         if sp is None:
             push(Item("mat", t=q, m=m, n_prims=cnt), last_touch[q])
             return
-        g, dl, z, x, y, dr = sp
+        g, dl, theta, dr, anti = sp
         scalar[0] *= g
         emit_phase((q,), dr, 0, early=True)
-        it = Item("mat", t=q, m=shear_matrix(z, x, y), n_prims=cnt)
-        it.sh = (z, x, y)
-        push(it, last_touch[q])
+        if theta != 0.0:
+            it = shear_item(q, theta)
+            it.n_prims = cnt
+            push(it, last_touch[q])
+            cnt = 0
         if keep_diag:
-            if dl != 1.0:
-                pending[q] = np.array([1.0, 0.0, 0.0, dl], dtype=complex)
+            if anti:
+                pending[q], pending_count[q] = np.array([0, -1, dl, 0], dtype=complex), cnt
+            elif dl != 1.0:
+                pending[q], pending_count[q] = np.array([1, 0, 0, dl], dtype=complex), cnt
         else:
-            emit_phase((q,), dl, 0, early=True)
+            emit_phase((q,), dl, cnt, early=True)
+
+    def settle(q: int):
+        """Leave at most a DIAGONAL factor pending on index bit q (before the wire is used as the control of a
+        non-diagonal gate, or leaves the shard)."""
+        m = pending[q]
+        if m is not None and not _is_diag(m):
+            flush(q)
 
     prims = fold_conjugated_phases(prims)
     pos = list(initial_pos) if initial_pos is not None else list(range(n))   # wire -> index bit of its data
@@ -455,8 +514,7 @@ def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = 
                 best, best_next = q, nxt
         # a pending non-diagonal 2x2 must be applied while its wire is still local
         for q in (best, top):
-            if pending[q] is not None and not _is_diag(pending[q]):
-                flush(q, keep_diag=True)
+            settle(q)
         if best != top:
             push(Item("perm", t=best, aux=top, n_prims=0))
             move(best, top)
@@ -468,8 +526,7 @@ def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = 
     for i_prim, p in enumerate(prims):
         if p.kind == "exchange":                  # from shard_schedule: wire p.target comes home, p.aux leaves
             gpos, lbit = pos[p.target], pos[p.aux]
-            if pending[lbit] is not None and not _is_diag(pending[lbit]):
-                flush(lbit, keep_diag=True)       # a non-diagonal 2x2 must be applied while its wire is local
+            settle(lbit)                      # a non-diagonal 2x2 must be applied while its wire is local
             push(Item("exchange", t=lbit, aux=gpos, n_prims=0))
             move(lbit, gpos)
             out.n_exchanges += 1
@@ -537,9 +594,7 @@ def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = 
             pending[tgt] = _HM if pending[tgt] is None else _mul(_HM, pending[tgt])
             continue
         for cq in ctrls:
-            m = pending[cq]
-            if m is not None and not _is_diag(m):
-                flush(cq, keep_diag=True)
+            settle(cq)
         flush(tgt)
         if p.kind == "x":
             push(Item("x", t=tgt, ctrls=ctrls))
@@ -595,7 +650,7 @@ def _cost(it: Item) -> float:
     """Rough DFMA-equivalents per amplitude."""
     if it.kind == "mat":
         if it.sh is not None:
-            return 3.0
+            return 2.0 if abs(it.sh) <= math.pi / 4 + 1e-15 else 3.0
         base = 4.0 if np.all(np.asarray(it.m).imag == 0) else 8.0
         return base / (1 << len(it.ctrls))
     if it.kind == "x":
@@ -779,7 +834,8 @@ class _Group:
 
     def __init__(self, r: int):
         self.r = r
-        self.sh: Dict[int, Tuple[float, float, float]] = {}     # register bit -> (z, x, y)
+        self.sh: Dict[int, float] = {}                           # register bit -> theta
+        self.par: Dict[int, Tuple[float, float, float, float, float]] = {}   # ... -> shear_params, once settled
         self.tab = np.ones(1 << r, dtype=complex)
         self.has_tab = False
         self.diag: Optional[dict] = None                         # a fan fused as the record's diag stage
@@ -819,6 +875,31 @@ class _Group:
                 self.tab[rho] *= f
         self.has_tab = True
 
+    def leftover(self) -> float:
+        """What the record's diagonal stage cannot put right after the in-place rotations (shear_params): the fused
+        fan only reaches the amplitudes with its bit set, so c_all is left for the pass to place."""
+        if self.sh and self.diag is not None:
+            (p,) = self.par.values()
+            return p[3]
+        return 1.0
+
+    def settle_rotations(self) -> None:
+        """Choose how the record's rotations run.  With a fused fan: two updates, the fan takes c_bit (fused_fan_scale)
+        and the pass c_all.  With a table for other reasons: two updates where the angle allows, c_all and c_bit go
+        into the table.  Otherwise three exact updates and no table (2k + 4 against 3k FP64 per amplitude, k <= 4)."""
+        if not self.sh:
+            return
+        if self.diag is not None:
+            return                                   # (par was set when the fan was fused)
+        for k, theta in self.sh.items():
+            p = shear_params(theta, exact=not self.has_tab)
+            self.par[k] = p
+            if p[3] != 1.0 or p[4] != 1.0:
+                self.tab *= p[3]
+                for rho in range(1 << self.r):
+                    if (rho >> k) & 1:
+                        self.tab[rho] *= p[4]
+
     def words_kw(self, prog: Program, r: int) -> Optional[dict]:
         kw: dict = {}
         p = self.sel_bits + [63] * (3 - len(self.sel_bits))          # 63: no such selector (reads as 0)
@@ -826,7 +907,7 @@ class _Group:
         if self.sh:
             pay: List[complex] = []
             for k in range(4):
-                z, x, y = self.sh.get(k, (0.0, 0.0, 0.0))
+                z, x, y = self.par.get(k, (0.0, 0.0, 0.0))[:3]
                 pay += [complex(z, x), complex(y, 0.0)]
             kw = dict(tk=T_LAYER, rm=sum(1 << k for k in self.sh) | sel, roff_t=prog.add_reals(pay))
         if self.has_tab:
@@ -856,7 +937,10 @@ class _Group:
 
 
 def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int, direct_io: bool = False,
-                direct_out: bool = False) -> None:
+                direct_out: bool = False, scale_in: complex = 1.0, final: bool = True) -> complex:
+    """Appends the pass to `prog`.  `scale_in` is a factor on every amplitude handed down by earlier passes (the
+    cos(theta) of rotations whose record had no table to take it, _Group.leftover); it goes into one of this pass's
+    tables if there is one.  Returns what is still left (1 when `final`: the pass then spends a record on it)."""
     a = len(ps.tile)
     tile = ps.tile
     loc = {q: i for i, q in enumerate(tile)}
@@ -929,6 +1013,7 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int, direct_io: bool
         return dict(j=jreg, dk=D_FANT, fid=fid, lm=lm, fm=fm, roff_d=prog.add_reals(list(lane_t) + list(warp_t)))
 
     encoded_rounds: List[Tuple[List[int], List[int]]] = []
+    round_slots: List[Tuple[List[int], List[_Group]]] = []
     for rd in ps.rounds:
         order = _thread_order(tile, rd.reg)
         slots: List[_Group] = [_Group(r)]
@@ -1004,13 +1089,15 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int, direct_io: bool
                 touch(touched, last_any[kt])
                 return
             has_reg_entries = any(k is not None for k in regs[1:])
-            if (kt is not None and (has_reg_entries or len(g.sh) == 1) and kt in g.sh and not g.has_tab
+            if (kt is not None and len(g.sh) == 1 and kt in g.sh and not g.has_tab and not g.sel_fans
                     and g.diag is None and not g.after and last_any[kt] == i):
-                # shears on bit kt followed at once by a fan with register AND other entries (the H + controlled-
-                # phase ladder of a QFT): the fan with its register table is the record's diag stage
+                # one rotation, on bit kt, followed at once by a fan on kt (the H + controlled-phase ladder of a QFT):
+                # the fan, with its register table if it has one, is the record's diag stage, and takes the 1 + t^2 the
+                # in-place rotation leaves on the amplitudes it multiplies anyway
                 fixed = [(1 << q, w) for q, w in entries.items() if q not in loc]
                 lw = {loc[q]: w for q, w in entries.items() if q in loc}
-                g.diag = fan_fields(order, fixed, w0, lw, t)
+                g.par[kt] = shear_params(g.sh[kt])
+                g.diag = fan_fields(order, fixed, w0 * g.par[kt][4], lw, t)
                 touch(touched, i)
                 return
             if kt is not None and has_reg_entries:
@@ -1050,6 +1137,8 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int, direct_io: bool
                 k = reg_index(it.t)
                 assert k is not None and not it.ctrls, "non-diagonal target outside the round's register bits"
                 i = last_any[k] + 1
+                while slot(i).diag is not None:      # (a record whose diag stage is a fused fan holds ONE rotation: the
+                    i += 1                           # fan takes that rotation's scale factor, nobody would take ours)
                 slot(i).sh[k] = it.sh
                 touch([k], i)
                 last_nd[k] = i
@@ -1086,6 +1175,23 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int, direct_io: bool
                        max([diag_min[k] for k in touched] + [0]))
             else:
                 emit_fan(it.t, it.w, dict(it.entries))
+        round_slots.append((order, slots))
+    # the rotations' scale factors: into the record's own table, else handed from record to record (and pass to pass)
+    # until a table takes them
+    left = complex(scale_in)
+    for order, slots in round_slots:
+        for g in slots:
+            g.settle_rotations()
+            left *= g.leftover()
+    if left != 1.0:
+        host = next((g for _, slots in round_slots for g in slots if g.has_tab), None)
+        if host is not None:
+            host.tab = host.tab * left
+            left = 1.0 + 0j
+        elif final or not 2.0 ** -40 < abs(left) < 2.0 ** 40:
+            scalars.append((0, left))
+            left = 1.0 + 0j
+    for order, slots in round_slots:
         gates: List[int] = []
         for g in slots:
             kw = g.words_kw(prog, r)
@@ -1128,6 +1234,7 @@ def encode_pass(prog: Program, ps: Pass, n: int, r: int, c: int, direct_io: bool
     woff = prog.add_words(words)
     prog.add_op(_lib.OP_TILE, woff=woff, wlen=len(words), nbytes=32.0 * 2 ** n)
     prog.n_prims += n_prims
+    return left
 
 
 def _emit_single(prog: Program, it: Item, n: int) -> None:
@@ -1204,6 +1311,7 @@ def plan(prims: Sequence[Prim], n_qubits: int, cfg: PlanConfig = DEFAULT, n_loca
     r = min(cfg.r, a)
     c = min(cfg.c, a if a == nl else a - 1)       # a tile smaller than the register needs at least one free bit
     remaining = list(norm.items)
+    carry = 1.0 + 0j                      # factor on every amplitude that no table has taken yet (encode_pass)
     while remaining:
         head = remaining[0]
         if head.kind == "swap":
@@ -1223,8 +1331,9 @@ def plan(prims: Sequence[Prim], n_qubits: int, cfg: PlanConfig = DEFAULT, n_loca
             ps, rest = build_pass(remaining, nl, a, r, c, cfg, pay_scale=scale)
             if not ps.rounds:                               # cannot happen: the head item always fits
                 raise RuntimeError(f"planner made no progress at {remaining[0]}")
+            last = all(it.kind in ("swap", "perm", "exchange") for it in rest)
             try:
-                encode_pass(prog, ps, nl, r, c, cfg.direct_io, cfg.direct_out)
+                carry = encode_pass(prog, ps, nl, r, c, cfg.direct_io, cfg.direct_out, scale_in=carry, final=last)
                 break
             except PassOverflow:
                 if scale == 1.0:

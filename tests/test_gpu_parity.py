@@ -275,10 +275,7 @@ def test_layer_record_with_table_variants_matches_interpreter(a):
     reg = [4, 5, 6, 7]
 
     def rot(q, t):
-        _, _, z, x, y, _ = P.split_shears(np.array([np.cos(t), -np.sin(t), np.sin(t), np.cos(t)], dtype=complex))
-        it = P.Item("mat", t=q, m=P.shear_matrix(z, x, y))
-        it.sh = (z, x, y)
-        return it
+        return P.shear_item(q, float(((t + np.pi / 2) % np.pi) - np.pi / 2))
 
     w = [np.exp(1j * x) for x in (0.4, 1.1, -0.8, 2.0)]
     layer = [rot(q, 0.3 + q) for q in reg] + [

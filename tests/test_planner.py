@@ -163,7 +163,7 @@ def _random_unitary(rng):
     return q.reshape(4)
 
 
-def test_split_shears_reproduces_unitaries_to_rounding():
+def test_split_rotation_reproduces_unitaries_to_rounding():
     rng = np.random.default_rng(5)
     h = np.array([1, 1, 1, -1], dtype=complex) / np.sqrt(2)
     mats = [_random_unitary(rng) for _ in range(2000)] + [h, -h, 1j * h]
@@ -174,23 +174,41 @@ def test_split_shears_reproduces_unitaries_to_rounding():
         a, b = rng.uniform(0, 6, 2)
         mats.append(np.array([np.cos(t), -np.exp(1j * a) * np.sin(t), np.exp(1j * b) * np.sin(t),
                               np.exp(1j * (a + b)) * np.cos(t)]) * np.exp(0.3j))
-    for m in mats:
-        sp = P.split_shears(m)
-        assert sp is not None
-        g, dl, z, x, y, dr = sp
-        assert abs(abs(g) - 1) < 1e-15 and abs(abs(dl) - 1) < 1e-15 and abs(abs(dr) - 1) < 1e-15
-        assert max(abs(z), abs(x), abs(y)) <= 1.0 + 1e-12   # |theta| <= pi/2: well conditioned shears
-        sm = P.shear_matrix(z, x, y)
-        rec = g * np.array([sm[0], sm[1] * dr, dl * sm[2], dl * sm[3] * dr])
-        assert np.max(np.abs(rec - m)) <= 2e-15
-        if np.all(m.imag == 0) and m[0] * m[3] - m[1] * m[2] > 0:
-            assert dl == 1 and dr == 1                        # a real rotation needs no phases at all
+    for allow_anti in (True, False):
+        n_anti = 0
+        for m in mats:
+            sp = P.split_rotation(m, allow_anti)
+            assert sp is not None
+            g, dl, theta, dr, anti = sp
+            assert abs(abs(g) - 1) < 1e-15 and abs(abs(dl) - 1) < 1e-15 and abs(abs(dr) - 1) < 1e-15
+            assert abs(theta) <= (np.pi / 4 if allow_anti else np.pi / 2) + 1e-12
+            z, x, y, c_all, c_bit = P.shear_params(theta)
+            assert max(abs(z), abs(x), abs(y)) <= 1.0 + 1e-12 and 0.5 - 1e-12 <= c_all <= 1 and 1 <= c_bit <= 2 + 1e-12
+            assert (y == 0.0) == (abs(theta) <= np.pi / 4 + 1e-15)
+            # the in-place updates followed by the two scale factors are the rotation
+            a0, a1 = np.array([1.0, 0.0]), np.array([0.0, 1.0])                         # rows of the accumulated matrix
+            a0 = a0 + z * a1
+            a1 = a1 + x * a0
+            if y:
+                a0 = a0 + y * a1
+            sm = np.array([a0[0] * c_all, a0[1] * c_all, a1[0] * c_all * c_bit, a1[1] * c_all * c_bit])
+            assert np.max(np.abs(sm - P.rotation_matrix(theta))) <= 1e-15
+            rm = P.rotation_matrix(theta)
+            if anti:
+                rm = P._mul(P._ANTI, rm)
+                n_anti += 1
+            rec = g * np.array([rm[0], rm[1] * dr, dl * rm[2], dl * rm[3] * dr])
+            assert np.max(np.abs(rec - m)) <= 3e-15
+            if np.all(m.imag == 0) and m[0] * m[3] - m[1] * m[2] > 0:
+                assert dl == 1 and dr == 1                        # a real rotation needs no phases at all
+        assert (0 < n_anti < len(mats)) if allow_anti else n_anti == 0
+    assert P.split_rotation(h)[4] is False                    # H is exactly R(pi / 4) . Z: no anti-diagonal left over
 
 
-def test_split_shears_rejects_non_unitary_matrices():
-    assert P.split_shears(np.array([1, 1, 0, 1], dtype=complex)) is None
-    assert P.split_shears(np.array([1, 0.5, 0.5, 1], dtype=complex)) is None
-    assert P.split_shears(np.array([2, 1j, 1j, 2], dtype=complex) / 2) is None
+def test_split_rotation_rejects_non_unitary_matrices():
+    assert P.split_rotation(np.array([1, 1, 0, 1], dtype=complex)) is None
+    assert P.split_rotation(np.array([1, 0.5, 0.5, 1], dtype=complex)) is None
+    assert P.split_rotation(np.array([2, 1j, 1j, 2], dtype=complex) / 2) is None
 
 
 def _records(prog):
@@ -265,12 +283,9 @@ def test_table_variants_absorb_phases_on_thread_and_fixed_bits():
     rng = np.random.default_rng(11)
     items, want_ops = [], []
     for q in reg:
-        t = 0.3 + q
-        _, _, z, x, y, _ = P.split_shears(np.array([np.cos(t), -np.sin(t), np.sin(t), np.cos(t)], dtype=complex))
-        it = P.Item("mat", t=q, m=P.shear_matrix(z, x, y))
-        it.sh = (z, x, y)
-        items.append(it)
-        want_ops.append(("mat", q, P.shear_matrix(z, x, y)))
+        t = 1.5 - 0.5 * q                               # two- and three-update rotations
+        items.append(P.shear_item(q, t))
+        want_ops.append(("mat", q, P.rotation_matrix(t)))
     w = [np.exp(1j * a) for a in (0.4, 1.1, -0.8, 2.0)]
     items += [P.Item("fan", t=4, w=1.0, entries={0: w[0]}),        # register bit x thread bit
               P.Item("fan", t=11, w=1.0, entries={6: w[1]}),       # target outside the tile, entry on a register bit

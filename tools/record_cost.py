@@ -26,9 +26,7 @@ def ry(t):
 
 
 def shear_item(q):
-    it = P.Item("mat", t=q, m=P.shear_matrix(0.3, -0.25, 0.3))
-    it.sh = (0.3, -0.25, 0.3)
-    return it
+    return P.shear_item(q, 0.29)
 
 
 def items_of(kind: str, k: int, n: int):
