@@ -487,26 +487,53 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
   const uint32_t lane_off = lane << 4, warp_off = (32u + (NWARP_T > 1 ? warp : 0u)) << 4;      // into a fan's tables
   c128* const fixp = S.fix[g];
   unsigned char* const pay_b = reinterpret_cast<unsigned char*>(S.pay);
-  // request tile j of this CTA into its buffer (warp 0 of a group; lanes = sub-copies)
+  // The sub-copies of a tile are issued by DIFFERENT warps of its group: a TMA instruction is a uniform-datapath
+  // op, so the lanes of one warp that issue one each are served one after the other (~110 cycles per copy: with all
+  // 32 copies of a scattered tile on warp 0, issuing cost the group 3-7 000 cycles per tile while its other warps
+  // waited at the barrier).  Thread (warp w, lane l) takes sub-copies l * NW + w, + NT, ...
+  constexpr uint32_t NW = NT / 32;
+  const int my_sub = (int)(lane * NW + warp);
+  // thread 0 of a group announces tile j of this CTA on its barrier ...
+  auto expect = [&](uint32_t j) {
+    if (blockIdx.x + (uint64_t)j * gridDim.x < n_tiles) mbar_expect_tx(&S.full[j % kStages][(j / kStages) & 1u], 16u << A);
+  };
+  // ... and, after a barrier of the group, every thread requests its sub-copies into the tile's buffer
   auto request = [&](uint32_t j) {
     const uint64_t tile = blockIdx.x + (uint64_t)j * gridDim.x;
-    if (tile >= n_tiles) return;
+    if (tile >= n_tiles || my_sub >= n_sub) return;
     const uint32_t s = j % kStages, u = j / kStages;
     uint64_t* const fb = &S.full[s][u & 1u];
-    if (lane == 0) mbar_expect_tx(fb, 16u << A);
-    __syncwarp();
     const uint64_t base = spread_tile(tile);
-    for (int sub = (int)lane; sub < n_sub; sub += 32) {
+    for (int sub = my_sub; sub < n_sub; sub += NT) {
       int c[5];
       coords(base, sub, c);
       tma_load5(S.stage[s] + (size_t)sub * tm.sub_amps, &tmap, fb, c);
     }
   };
-  if (!init && tid < 32) {          // prologue: the first three tiles
+  auto store_tile = [&](const c128* buf, uint64_t base) {
+    for (int sub = my_sub; sub < n_sub; sub += NT) {
+      int c[5];
+      coords(base, sub, c);
+      tma_store5(&tmap, buf + (size_t)sub * tm.sub_amps, c);
+    }
+    bulk_commit();
+  };
+  if (!init && g == 0) {            // prologue: the first three tiles
+    if (t == 0)
+      for (uint32_t j = 0; j < (uint32_t)kStages; ++j) expect(j);
+    group_sync<NT>(0);
     for (uint32_t j = 0; j < (uint32_t)kStages; ++j) request(j);
   }
-  bool store_pending = false;       // warp 0: the previous tile's store has not been waited for yet
-  uint32_t j_prev = 0;
+  if (init) {
+    // A pass that starts from a basis state: every tile but one is all zeros and stays all zeros (the pass is
+    // linear), so those tiles are TMA stores from a buffer of zeros that is written once -- the pass moves 16 * 2^n
+    // bytes and computes one tile.
+#pragma unroll
+    for (int i = 0; i < PER; ++i) S.stage[g][t + (uint32_t)i * NT] = make_double2(0.0, 0.0);
+    fence_async();
+    group_sync<NT>(g);
+  }
+  bool store_pending = false;       // this group's previous tile has been handed to the TMA unit, not yet waited for
   // B200_TILE_TIMING=1: thread 0 of every group accumulates the cycles it spends in each phase of a tile
   long long tk0 = TIMING ? clock64() : 0;
   auto tick = [&](int phase) {
@@ -519,58 +546,62 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
   for (uint32_t j = g;; j += kGroups) {
     const uint64_t tile = blockIdx.x + (uint64_t)j * gridDim.x;
     if (tile >= n_tiles) break;
-    // an initial pass synthesises its tiles and never shares a buffer between the groups
-    const uint32_t s = init ? g : j % kStages, u = j / kStages;
+    if (init && tile != init_tile) {
+      store_tile(S.stage[g], spread_tile(tile));
+      asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory");
+      tick(8);
+      continue;
+    }
+    // the one computed tile of an initial pass has the third buffer to itself
+    const uint32_t s = init ? 2u : j % kStages, u = j / kStages;
     const uint64_t fixedidx = spread_tile(tile) | index_offset;
     const uint32_t fx_lo = (uint32_t)fixedidx, fx_hi = (uint32_t)(fixedidx >> 32);
-    // per-tile fixed-bit products of the fans, while the tile is still in flight (one warp per fan)
-    for (int f = (int)warp; f < n_fans; f += (NT >> 5)) {
+    // per-tile fixed-bit products of the fans, while the tile is still in flight (eight lanes per fan)
+    for (int f = (int)(4u * warp + (lane >> 3)); f < n_fans; f += (int)(4u * NW)) {
       const uint32_t off = (uint32_t)S.fanw[f] - dir_off;
       const uint64_t rec = S.fanw[off];
       const int ne = (int)(rec & 0xFFFFFFFFu);
       const double2* __restrict__ w = reinterpret_cast<const double2*>(S.pay + ((uint32_t)(rec >> 32) - pay_lo));
       c128 p = make_double2(1.0, 0.0);
-      for (int e = (int)lane; e < ne; e += 32) {
+      for (int e = (int)(lane & 7u); e < ne; e += 8) {
         const uint64_t m = S.fanw[off + 1 + e];
         if ((fixedidx & m) == m) p = cmul(p, w[1 + e]);
       }
+      const uint32_t seg = 0xFFu << (lane & 24u);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+      for (int o = 4; o > 0; o >>= 1) {
         c128 q;
-        q.x = __shfl_xor_sync(0xffffffffu, p.x, o);
-        q.y = __shfl_xor_sync(0xffffffffu, p.y, o);
+        q.x = __shfl_xor_sync(seg, p.x, o);
+        q.y = __shfl_xor_sync(seg, p.y, o);
         p = cmul(p, q);
       }
-      if (lane == 0) fixp[f] = cmul(p, w[0]);
+      if ((lane & 7u) == 0) fixp[f] = cmul(p, w[0]);
     }
     tick(0);                        // fan products
-    // the previous tile's store has had the time of the fan products to read its buffer: wait for it and request the
-    // tile that uses the buffer next (for the other group)
-    if (warp == 0 && store_pending) {
+    // the previous tile's stores have had the time of the fan products to read their buffer
+    if (store_pending) {
       bulk_wait_read();
-      __syncwarp();
-      if (!init) request(j_prev + kStages);
-      store_pending = false;
+      if (t == 0 && !init) expect(j - kGroups + kStages);
     }
-    tick(1);                        // wait for the previous store's reads + request the next tile
+    tick(1);                        // wait for the previous stores' reads
     // (this barrier also keeps the threads of a group within one tile of each other: a parity wait cannot tell phase
     // u from u + 2)
     group_sync<NT>(g);
     tick(2);                        // group barrier
+    // the previous tile's buffer is free: request the tile that uses it next (j + 1, for the OTHER group)
+    if (store_pending && !init) request(j - kGroups + kStages);
+    store_pending = false;
     unsigned char* const smb = reinterpret_cast<unsigned char*>(S.stage[s]);
     if (init) {
 #pragma unroll
       for (int i = 0; i < PER; ++i) *reinterpret_cast<c128*>(smb + ((t + (uint32_t)i * NT) << 4)) = make_double2(0.0, 0.0);
-      if (tile == init_tile) {
-        group_sync<NT>(g);
-        if (t == 0) S.stage[s][swz(init_local)] = make_double2(1.0, 0.0);
-      }
+      group_sync<NT>(g);
+      if (t == 0) S.stage[s][swz(init_local)] = make_double2(1.0, 0.0);
       group_sync<NT>(g);
     } else {
       mbar_wait(&S.full[s][u & 1u], (u >> 1) & 1u);
     }
-    tick(3);                        // wait for the tile
-
+    tick(3);                        // request + wait for the tile
     c128 v[PER];
     for (int rd = 0; rd < n_rounds; ++rd) {
       const uint4 hq = *reinterpret_cast<const uint4*>(&S.rh[rd]);
@@ -684,20 +715,12 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
       group_sync<NT>(g);
       tick(7);                      // round: barrier
     }
-    // the finished tile leaves through the TMA unit (warp 0 of the group; lanes = sub-copies)
-    if (warp == 0) {
-      for (int sub = (int)lane; sub < n_sub; sub += 32) {
-        int c[5];
-        coords(fixedidx ^ index_offset, sub, c);
-        tma_store5(&tmap, S.stage[s] + (size_t)sub * tm.sub_amps, c);
-      }
-      bulk_commit();
-      store_pending = true;
-      j_prev = j;
-    }
-    tick(8);                        // issue the store
+    // the finished tile leaves through the TMA unit (every warp of the group issues its share of the sub-copies)
+    store_tile(S.stage[s], fixedidx ^ index_offset);
+    store_pending = true;
+    tick(8);                        // issue the stores
   }
-  if (warp == 0 && store_pending) bulk_wait_all();
+  bulk_wait_all();
 }
 
 // ---- host side: the tile as a tensor box -------------------------------------------------------------------------
