@@ -578,19 +578,14 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
       if ((lane & 7u) == 0) fixp[f] = cmul(p, w[0]);
     }
     tick(0);                        // fan products
-    // the previous tile's stores have had the time of the fan products to read their buffer
-    if (store_pending) {
-      bulk_wait_read();
-      if (t == 0 && !init) expect(j - kGroups + kStages);
-    }
-    tick(1);                        // wait for the previous stores' reads
+    // announce the tile that will use the previous tile's buffer next (j + 1, for the OTHER group); its sub-copies are
+    // requested below, thread by thread
+    if (store_pending && t == 0 && !init) expect(j - kGroups + kStages);
+    tick(1);
     // (this barrier also keeps the threads of a group within one tile of each other: a parity wait cannot tell phase
     // u from u + 2)
     group_sync<NT>(g);
     tick(2);                        // group barrier
-    // the previous tile's buffer is free: request the tile that uses it next (j + 1, for the OTHER group)
-    if (store_pending && !init) request(j - kGroups + kStages);
-    store_pending = false;
     unsigned char* const smb = reinterpret_cast<unsigned char*>(S.stage[s]);
     if (init) {
 #pragma unroll
@@ -601,7 +596,7 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
     } else {
       mbar_wait(&S.full[s][u & 1u], (u >> 1) & 1u);
     }
-    tick(3);                        // request + wait for the tile
+    tick(3);                        // wait for the tile
     c128 v[PER];
     for (int rd = 0; rd < n_rounds; ++rd) {
       const uint4 hq = *reinterpret_cast<const uint4*>(&S.rh[rd]);
@@ -618,7 +613,16 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
           v[i ^ (i >> 1)] = *reinterpret_cast<const c128*>(smb + so);
         }
       }
-      tick(4);                      // round: registers <- shared memory (issue)
+      // Sub-copy i of a tile is stored and loaded by the same thread and occupies the same part of the buffer, so a
+      // thread may refill its part as soon as ITS store has read it -- no barrier.  (Draining 64 KB takes the TMA unit
+      // ~4 000 cycles, so there is still a wait here; leaving the refill until later in the round -- a test inside the
+      // record loop -- cost more in the loop than the wait: 208 against 183 ms on the 30-qubit layer circuit.)
+      if (store_pending) {
+        bulk_wait_read();
+        if (!init) request(j - kGroups + kStages);
+        store_pending = false;
+      }
+      tick(4);                      // round: registers <- shared memory (issue), refill of the previous buffer
       // the next record is fetched while the current one runs
       uint4 q = S.rec[first];
       for (int gi = first; gi < first + ng; ++gi) {
