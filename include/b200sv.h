@@ -104,6 +104,12 @@ int b200_scale(b200_state* st, double re, double im);
 /* First amplitude with |a| > eps in index order (utils.ignore_global_phase, utils.py:130-144).
    *index = UINT64_MAX when there is none. */
 int b200_first_above(b200_state* st, double eps, uint64_t* index, double* re, double* im);
+/* The same search for a shard whose wires sit on permuted index bits (sharded states keep the layout their swaps and
+   exchanges left): *key = the smallest WIRE-order index of an amplitude of this shard with |a| > eps, where bit p of
+   (index_offset | local index) is wire wire_of_bit[p] (a permutation of 0..n_bits-1, n_bits <= 40 covering the whole
+   register); UINT64_MAX when there is none.  The caller takes the minimum over the shards and reads the amplitude
+   with b200_state_download. */
+int b200_first_above_wire(b200_state* st, double eps, const int32_t* wire_of_bit, int n_bits, uint64_t* key);
 
 /* Batched terminal-measurement sampler.  For each shot s, walks the measured qubits in `order`
    (the reference's target_iter order), comparing uniforms[s*m + j] with the conditional probability

@@ -155,6 +155,15 @@ class OracleState:
             return None
         return int(hit[0]), complex(self.psi[hit[0]])
 
+    def first_above_wire(self, eps, wire_of_bit):
+        hit = np.nonzero(np.abs(self.psi) > eps)[0].astype(np.int64) | np.int64(self.index_offset)
+        if hit.size == 0:
+            return None
+        key = np.zeros_like(hit)
+        for p, w in enumerate(wire_of_bit):
+            key |= ((hit >> p) & 1) << int(w)
+        return int(key.min())
+
     def sample(self, order: Sequence[int], uniforms: np.ndarray) -> np.ndarray:
         """Same descent as csrc/sample.cu: conditional probabilities on the uncollapsed state."""
         order = list(order)

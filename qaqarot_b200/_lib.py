@@ -64,6 +64,7 @@ _SIGNATURES = {
     "b200_norm2": (C.c_int, [C.c_void_p, _P(C.c_double)]),
     "b200_scale": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "b200_first_above": (C.c_int, [C.c_void_p, C.c_double, _P(C.c_uint64), _P(C.c_double), _P(C.c_double)]),
+    "b200_first_above_wire": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_int, _P(C.c_uint64)]),
     "b200_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "b200_expect_group": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                     _P(C.c_double), _P(C.c_double)]),

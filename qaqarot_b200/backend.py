@@ -501,6 +501,24 @@ class ShardedB200Backend(B200Backend):
         self.group = group
         self._host_state_factory = host_state_factory
 
+    GATHER_LIMIT = 30               # ShardedState.download gathers 2^n amplitudes on every host
+
+    def run(self, gates, n_qubits, shots=None, initial=None, returns=None, **kwargs):
+        # refuse BEFORE the circuit runs what could only fail after it: a register this large does not come back as
+        # one ndarray (use shots=, hamiltonian=, returns="_inner_ctx" + device_state.download_shard()/save())
+        wants_vector = (returns in ("statevector", "statevector_and_shots")
+                        or (returns is None and shots is None and kwargs.get("hamiltonian") is None))
+        if n_qubits > self.GATHER_LIMIT and wants_vector:
+            raise ValueError(f"a sharded {n_qubits}-qubit statevector is not gathered on the host (limit "
+                             f"{self.GATHER_LIMIT}): ask for shots=, hamiltonian=, or returns='_inner_ctx' and read "
+                             f"device_state.download_shard() / device_state.save(directory)")
+        return super().run(gates, n_qubits, shots=shots, initial=initial, returns=returns, **kwargs)
+
+    def _download(self, st):
+        if st.n_qubits > self.GATHER_LIMIT:          # returns="_inner_ctx": the context carries the device state only
+            return None
+        return super()._download(st)
+
     def copy(self) -> "ShardedB200Backend":
         other = ShardedB200Backend(self.device, self.plan_config, self.group, self._host_state_factory)
         if self.cache is not None:

@@ -221,6 +221,36 @@ __global__ void __launch_bounds__(kThreads) k_first_above(const c128* __restrict
   if (best != ~0ull) atomicMin(out, best);
 }
 
+// The same search in *wire* order for a state whose wires sit on permuted index bits (sharded states never undo
+// their layout): key(i) = sum of bit p of (index_offset | i) << wire_of_bit[p], found through five 256-entry tables;
+// the smallest key wins.  A full scan: a smaller physical index does not mean a smaller key.
+struct WireOfBit { int8_t w[40]; };
+__global__ void __launch_bounds__(kThreads) k_first_above_wire(const c128* __restrict__ amp, uint64_t dim, uint64_t offset,
+                                                               double eps2, WireOfBit wob, int n_bits,
+                                                               unsigned long long* __restrict__ out) {
+  __shared__ unsigned long long tab[5][256];
+  for (int idx = threadIdx.x; idx < 5 * 256; idx += blockDim.x) {
+    const int c = idx >> 8, v = idx & 255;
+    unsigned long long k = 0;
+    for (int b = 0; b < 8; ++b)
+      if (((v >> b) & 1) && 8 * c + b < n_bits) k |= 1ull << wob.w[8 * c + b];
+    tab[c][v] = k;
+  }
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  unsigned long long best = ~0ull;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += stride) {
+    const c128 a = amp[i];
+    if (a.x * a.x + a.y * a.y > eps2) {
+      const uint64_t f = offset | i;
+      const unsigned long long k = tab[0][f & 255] | tab[1][(f >> 8) & 255] | tab[2][(f >> 16) & 255] |
+                                   tab[3][(f >> 24) & 255] | tab[4][(f >> 32) & 255];
+      best = k < best ? k : best;
+    }
+  }
+  if (best != ~0ull) atomicMin(out, best);
+}
+
 // ---- batched sampler ----------------------------------------------------------------------------------
 // Conditional marginal for one measured qubit: for every pending shot group g (amplitudes whose already
 // measured qubits equal that group's outcomes) accumulate ||psi[.., bit=0]||^2 and ||psi[..]||^2.
@@ -653,6 +683,31 @@ int b200_first_above(b200_state* st, double eps, uint64_t* index, double* re, do
     *re = st->h_result[0];
     *im = st->h_result[1];
   }
+  return 0;
+}
+
+int b200_first_above_wire(b200_state* st, double eps, const int32_t* wire_of_bit, int n_bits, uint64_t* key) {
+  B200_REQUIRE(st != nullptr && wire_of_bit != nullptr && key != nullptr, "b200_first_above_wire: null argument");
+  B200_REQUIRE(n_bits >= st->n && n_bits <= 40, "b200_first_above_wire: n_bits must cover the shard and stay below 41");
+  WireOfBit wob;
+  uint64_t seen = 0;
+  for (int b = 0; b < n_bits; ++b) {
+    B200_REQUIRE(wire_of_bit[b] >= 0 && wire_of_bit[b] < n_bits && !((seen >> wire_of_bit[b]) & 1),
+                 "b200_first_above_wire: wire_of_bit is not a permutation");
+    seen |= 1ull << wire_of_bit[b];
+    wob.w[b] = (int8_t)wire_of_bit[b];
+  }
+  B200_CUDA(cudaSetDevice(st->device));
+  unsigned long long* d_out = reinterpret_cast<unsigned long long*>(st->d_result + 4);
+  B200_CUDA(cudaMemsetAsync(d_out, 0xff, sizeof(unsigned long long), st->stream));
+  k_first_above_wire<<<reduce_blocks(st->dim), kThreads, 0, st->stream>>>(st->amp, st->dim, st->index_offset, eps * eps, wob,
+                                                                         n_bits, d_out);
+  st->launches++;
+  B200_CUDA(cudaGetLastError());
+  unsigned long long* h_out = reinterpret_cast<unsigned long long*>(st->h_result + 4);
+  B200_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st->stream));
+  B200_CUDA(cudaStreamSynchronize(st->stream));
+  *key = *h_out;
   return 0;
 }
 

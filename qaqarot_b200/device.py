@@ -127,6 +127,14 @@ class DeviceState:
             return None
         return idx.value, complex(re.value, im.value)
 
+    def first_above_wire(self, eps: float, wire_of_bit: Sequence[int]) -> Optional[int]:
+        """Smallest wire-order index of an amplitude of this shard above eps (bit p of the full index is wire
+        wire_of_bit[p]); None when there is none."""
+        wob = np.ascontiguousarray(wire_of_bit, dtype=np.int32)
+        key = C.c_uint64()
+        _lib.check(self._lib.b200_first_above_wire(self._h, eps, wob.ctypes.data_as(C.c_void_p), int(wob.size), C.byref(key)))
+        return None if key.value == 0xFFFFFFFFFFFFFFFF else int(key.value)
+
     def sample(self, order: Sequence[int], uniforms: np.ndarray) -> np.ndarray:
         """uniforms: (n_shots, m) float64 -> (n_shots,) uint64, bit j set when qubit order[j] read 1."""
         order = np.ascontiguousarray(order, dtype=np.int32)

@@ -1352,3 +1352,58 @@ def _emit_restore(prog: Program, norm: Normalized, n: int) -> None:
         woff = prog.add_words([p | (q << 8) for p, q in pairs])
         prog.add_op(_lib.OP_PERMUTE, woff=woff, wlen=len(pairs), nbytes=32.0 * 2 ** n)
     prog.n_prims += norm.n_relabelled
+
+
+def describe_tile_pass(words, woff: int, n: int, reals) -> dict:
+    """What one encoded TILE pass asks of csrc/tile.cu: rounds, records by kind, and the FP64 instructions per amplitude
+    the kernel executes for it (bench.py's FP64 roofline, tools/plan_stats.py)."""
+    h0 = words[woff]
+    a, r, n_rounds = h0 & 0xFF, (h0 >> 16) & 0xFF, (h0 >> 24) & 0xFF
+    tile = [((words[woff + 1 + i // 8]) >> (8 * (i % 8))) & 0xFF for i in range(a)]
+    runs, prev = 0, None
+    for q in tile[3:]:
+        runs += prev is None or q != prev + 1
+        prev = q
+    pos = woff + (words[woff + 3] >> 32)
+    per = 1 << r
+    out = dict(a=a, rounds=n_rounds, runs=runs, records=0, layers=0, rotations=0, rot3=0, tabs=0, fans=0, other=0, fp64=0.0,
+               conflict_rounds=0, tile=tile)
+    for _ in range(n_rounds):
+        ng, nw = words[pos] & 0xFFFF, words[pos] >> 16
+        order = [((words[pos + 1 + i // 8]) >> (8 * (i % 8))) & 0xFF for i in range(a)]
+        lanes = order[r:r + 3]
+        classes = {(b % 3) for b in lanes if b < 6}
+        if len(classes) < 3:
+            out["conflict_rounds"] += 1
+        for g in range(ng):
+            g0 = words[pos + 3 + 3 * g]
+            tk, j, dk, rm = g0 & 0xFF, (g0 >> 8) & 0xFF, (g0 >> 16) & 0xFF, (g0 >> 48) & 0xFFFF
+            out["records"] += 1
+            f = 0.0
+            if tk == T_LAYER:
+                k = bin(rm & 15).count("1")
+                out["layers"] += 1
+                out["rotations"] += k
+                roff = words[pos + 5 + 3 * g] & 0xFFFFFFFF
+                for b in range(4):                # 4 or 6 DFMA per pair (third shear only when y != 0)
+                    if (rm >> b) & 1:
+                        three = reals[roff + 4 * b + 2] != 0.0
+                        out["rot3"] += three
+                        f += 3.0 if three else 2.0
+            elif tk in (T_MATC, T_MATR):
+                f += 8.0 if tk == T_MATC else 4.0
+                out["other"] += 1
+            elif tk == T_X:
+                out["other"] += 1
+            if dk == D_TAB:
+                out["tabs"] += 1
+                f += 4.0
+            elif dk in (D_FAN, D_FANT, D_W, D_FIX):
+                out["fans"] += 1
+                frac = 0.5 if j < r else 1.0
+                f += frac * (8.0 if dk == D_FAN else 4.0) + 8.0 / per
+            elif dk == D_PHASE:
+                f += 4.0 / (1 << bin(rm).count("1"))
+            out["fp64"] += f
+        pos += nw
+    return out

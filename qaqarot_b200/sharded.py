@@ -103,6 +103,7 @@ class ShardedState:
     Every rank must make the same calls in the same order."""
 
     BOUNCE_AMPS = 1 << 24           # 256 MiB bounce buffer for exchanges
+    MIN_LOCAL = 9                   # smallest tile csrc/tile.cu is built for (planner.PlanConfig.kernel_tiles)
 
     def __init__(self, n_qubits: int, device: Optional[int] = None, group=None, host_state_factory=None):
         torch, dist = _torch()
@@ -116,6 +117,9 @@ class ShardedState:
             raise ValueError(f"world size {self.world} is not a power of two")
         if n_qubits - g < 1:
             raise ValueError(f"{n_qubits} qubits cannot be sharded over {self.world} ranks")
+        if host_state_factory is None and n_qubits - g < self.MIN_LOCAL:
+            raise ValueError(f"{n_qubits} qubits over {self.world} GPUs leaves {n_qubits - g} local qubits; the fused tile "
+                             f"pass needs at least {self.MIN_LOCAL} (use B200Backend on one GPU for registers this small)")
         self.n_qubits = n_qubits
         self.n_global = g
         self.n_local = n_qubits - g
@@ -224,37 +228,87 @@ class ShardedState:
     # -- checkpoints (a 33-36 qubit state cannot return through one ndarray) -------------------
     CHECKPOINT_FORMAT = "b200sv-sharded-v1"
 
+    CHECKPOINT_CHUNK = 1 << 24       # amplitudes per transfer (256 MiB): a 128 GiB shard never sits in host memory
+
+    def _all_ok(self, ok: bool, what: str) -> None:
+        """Collective agreement before anything irreversible: every rank raises together or none does."""
+        bad = self._allreduce(np.array([0.0 if ok else 1.0]))[0]
+        if bad:
+            raise ValueError(f"{what} ({int(bad)} of {self.world} ranks failed" + ("" if ok else ", this one included") + ")")
+
     def save(self, directory: str) -> None:
-        """Every rank writes its shard as raw little-endian complex128 (`shard_<rank>.c128`, physical index order);
-        rank 0 writes `header.json` with the register size, the world size and the wire -> index-bit layout, without
-        which the shards cannot be interpreted (swap gates and exchanges only relabel wires)."""
+        """Every rank streams its shard as raw little-endian complex128 (`shard_<rank>.c128`, physical index order) in
+        256 MiB pieces; rank 0 then writes `header.json` -- register size, world size, wire -> index-bit layout, without
+        which the shards cannot be interpreted (swap gates and exchanges only relabel wires) -- to a temporary name and
+        renames it into place last, so a directory with a header is a complete checkpoint."""
         import json
         import os
         _, dist = _torch()
-        if self.rank == 0:
-            os.makedirs(directory, exist_ok=True)
+        err = None
+        try:
+            if self.rank == 0:
+                os.makedirs(directory, exist_ok=True)
+                try:
+                    os.remove(os.path.join(directory, "header.json"))         # an old header must not bless new shards
+                except FileNotFoundError:
+                    pass
+        except OSError as e:
+            err = e
         dist.barrier(group=self.group)
-        self.st.download().astype("<c16", copy=False).tofile(os.path.join(directory, f"shard_{self.rank}.c128"))
+        if err is None:
+            try:
+                total, chunk = 1 << self.n_local, self.CHECKPOINT_CHUNK
+                with open(os.path.join(directory, f"shard_{self.rank}.c128"), "wb") as f:
+                    for off in range(0, total, chunk):
+                        self.st.download(off, min(chunk, total - off)).astype("<c16", copy=False).tofile(f)
+                    f.flush()
+                    os.fsync(f.fileno())
+            except OSError as e:
+                err = e
+        self._all_ok(err is None, f"checkpoint {directory}: writing a shard failed: {err}")
         if self.rank == 0:
-            with open(os.path.join(directory, "header.json"), "w") as f:
+            tmp = os.path.join(directory, "header.json.tmp")
+            with open(tmp, "w") as f:
                 json.dump({"format": self.CHECKPOINT_FORMAT, "n_qubits": self.n_qubits, "world": self.world,
                            "n_local": self.n_local, "dtype": "complex128", "byteorder": "little",
                            "layout_wire_to_index_bit": list(self.layout)}, f)
+                f.flush()
+                os.fsync(f.fileno())
+            os.replace(tmp, os.path.join(directory, "header.json"))
         dist.barrier(group=self.group)
 
     def load(self, directory: str) -> None:
-        """Restore a checkpoint written by `save` on the same world size (shards are not re-cut)."""
+        """Restore a checkpoint written by `save` on the same world size (shards are not re-cut).  Header and shard
+        sizes are validated on every rank and agreed on collectively before the state is touched."""
         import json
         import os
-        with open(os.path.join(directory, "header.json")) as f:
-            h = json.load(f)
-        if h.get("format") != self.CHECKPOINT_FORMAT or h["n_qubits"] != self.n_qubits or h["world"] != self.world:
-            raise ValueError(f"checkpoint {directory} does not match this register: {h}")
-        shard = np.fromfile(os.path.join(directory, f"shard_{self.rank}.c128"), dtype="<c16")
-        if shard.size != 1 << self.n_local:
-            raise ValueError(f"shard_{self.rank}.c128 has {shard.size} amplitudes, expected {1 << self.n_local}")
-        self.st.upload(shard.astype(np.complex128, copy=False))
-        self.layout = [int(b) for b in h["layout_wire_to_index_bit"]]
+        problem, h = None, {}
+        try:
+            with open(os.path.join(directory, "header.json")) as f:
+                h = json.load(f)
+            layout = [int(b) for b in h.get("layout_wire_to_index_bit", [])]
+            if h.get("format") != self.CHECKPOINT_FORMAT:
+                problem = f"unknown format {h.get('format')!r}"
+            elif (h.get("n_qubits"), h.get("world"), h.get("n_local")) != (self.n_qubits, self.world, self.n_local):
+                problem = (f"written for {h.get('n_qubits')} qubits on {h.get('world')} ranks ({h.get('n_local')} local), this "
+                           f"register has {self.n_qubits} on {self.world} ({self.n_local} local)")
+            elif h.get("dtype") != "complex128" or h.get("byteorder") != "little":
+                problem = f"dtype {h.get('dtype')!r} / byteorder {h.get('byteorder')!r} not supported"
+            elif sorted(layout) != list(range(self.n_qubits)):
+                problem = "layout_wire_to_index_bit is not a permutation of the index bits"
+            else:
+                size = os.path.getsize(os.path.join(directory, f"shard_{self.rank}.c128"))
+                if size != 16 << self.n_local:
+                    problem = f"shard_{self.rank}.c128 has {size} bytes, expected {16 << self.n_local}"
+        except (OSError, ValueError, TypeError) as e:
+            problem = str(e)
+        self._all_ok(problem is None, f"checkpoint {directory} cannot be loaded: {problem}")
+        total, chunk = 1 << self.n_local, self.CHECKPOINT_CHUNK
+        with open(os.path.join(directory, f"shard_{self.rank}.c128"), "rb") as f:
+            for off in range(0, total, chunk):
+                part = np.fromfile(f, dtype="<c16", count=min(chunk, total - off))
+                self.st.upload(part.astype(np.complex128, copy=False), off)
+        self.layout = layout
 
     def copy_from(self, other: "ShardedState") -> None:
         self.st.copy_from(other.st)
@@ -373,6 +427,9 @@ class ShardedState:
         """Bring every wire in `wires` onto a local index bit (used by X / Y expectation values)."""
         need = [w for w in wires if self.layout[w] >= self.n_local]
         keep = set(self.layout[w] for w in wires)
+        if len(set(wires)) > self.n_local:
+            raise ValueError(f"a Pauli term with X/Y on {len(set(wires))} qubits does not fit the {self.n_local} local qubits "
+                             f"of a shard")
         for w in need:
             inv = self._wire_at()
             victim = max(p for p in range(self.n_local) if p not in keep)
@@ -422,11 +479,28 @@ class ShardedState:
         self.st.scale(z)
 
     def first_above(self, eps: float) -> Optional[Tuple[int, complex]]:
-        vec = self.download()
-        hit = np.nonzero(np.abs(vec) > eps)[0]
-        if hit.size == 0:
+        """(wire-order index, amplitude) of the first amplitude above eps, without gathering the register: every shard
+        searches its own amplitudes for the smallest wire-order index (b200_first_above_wire), the minimum over the
+        ranks wins and its owner publishes the amplitude."""
+        key = self.st.first_above_wire(eps, self._wire_at())
+        none = float(1 << 62)
+        keys = self._allgather_scalar(float(key) if key is not None else none)      # exact: keys are below 2^53
+        best = min(keys)
+        if best >= none:
             return None
-        return int(hit[0]), complex(vec[hit[0]])
+        best = int(best)
+        phys = self._phys_index(best)
+        val = np.zeros(2)
+        if phys >> self.n_local == self.rank:
+            a = self.st.download(phys & ((1 << self.n_local) - 1), 1)[0]
+            val[:] = (a.real, a.imag)
+        val = self._allreduce(val)
+        return best, complex(val[0], val[1])
+
+    def _allgather_scalar(self, x: float) -> List[float]:
+        v = np.zeros(self.world)
+        v[self.rank] = x
+        return [float(t) for t in self._allreduce(v)]
 
     def sample(self, order: Sequence[int], uniforms: np.ndarray) -> np.ndarray:
         """The descent of csrc/sample.cu with the per-level sums added over the shards."""

@@ -20,7 +20,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
 
 
+def _cuda_devices() -> int:
+    try:
+        from qaqarot_b200 import _lib
+        return _lib.device_count()
+    except Exception:
+        return 0
+
+
 def pytest_collection_modifyitems(config, items):
+    if any("gpu" in item.keywords for item in items) and _cuda_devices() == 0:
+        # (the library itself never falls back: test_backend_requires_the_cuda_library checks that on the GPU box)
+        no_gpu = pytest.mark.skip(reason="no CUDA device (or libb200sv.so not built)")
+        for item in items:
+            if "gpu" in item.keywords:
+                item.add_marker(no_gpu)
     if os.path.isdir(os.path.join(REFERENCE, "blueqat")):
         return
     skip = pytest.mark.skip(reason="/root/reference not present")

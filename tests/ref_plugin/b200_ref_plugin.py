@@ -1,12 +1,13 @@
 """pytest plugin used by tests/test_reference_suite.py: makes "b200" blueqat's default backend before the
 reference's own tests/conftest.py reads it.  The device is the numpy interpreter of the op program
-(no GPU in the build container); on a GPU box drop the state_factory argument."""
+(no GPU in the build container); with B200_REF_SUITE_DEVICE=cuda it is the CUDA library (GPU box, blueqat from
+baseline/_ref through B200_REF_ROOT)."""
 import os
 import sys
 import warnings
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-sys.path.insert(0, "/root/reference")
+sys.path.insert(0, os.environ.get("B200_REF_ROOT", "/root/reference"))
 warnings.simplefilter("ignore", SyntaxWarning)
 
 from blueqat import BlueqatGlobalSetting  # noqa: E402

@@ -17,6 +17,7 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "gates/sec" and d["unit"] == "gates/s" and d["value"] > 0
     assert d["higher_is_better"] is True and d["vs_baseline"] is None
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline"]["host_logical_cores"] == os.cpu_count() and d["config"]["n_qubits"] == 14
     assert d["e2e"] == {"value": d["value"], "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
@@ -27,12 +28,25 @@ def test_other_ranks_of_the_reference_arm_exit_quietly():
     assert res.returncode == 0 and res.stdout.strip() == ""
 
 
-def test_cpu_sample_is_stratified():
+def test_cpu_sample_holds_every_gate_kind_at_every_size():
     sys.path.insert(0, ROOT)
     import bench
     from qaqarot_b200 import workloads as W
-    picked, desc = bench.cpu_sample(W.qft(30), 30, 40.0)
-    kinds = {o.lowername for o in picked}
-    assert "h" in kinds and "cphase" in kinds and len(picked) < 40
-    picked, _ = bench.cpu_sample(W.qft(12), 12, 1e9)
-    assert len(picked) == len(W.qft(12).ops)
+    for wname, n, depth, budget in (("qft", 30, 0, 20.0), ("layers", 30, 20, 20.0), ("layers", 33, 8, 4.0),
+                                    ("layers", 36, 8, 4.0), ("qaoa", 28, 0, 10.0)):
+        n_cpu, circ, picked = bench.cpu_plan(wname, n, depth, budget)
+        want = {o.lowername for o in bench.build_workload(wname, n, depth)[0].ops}
+        assert {o.lowername for o in picked} == want, (wname, n)
+        assert 16 <= n_cpu <= min(n, 30)
+        cost = sum(bench.CPU_COST_26.get(o.lowername, 0.9) * 2.0 ** (n_cpu - 26) for o in picked)
+        assert cost <= 1.5 * budget, (wname, n, n_cpu, cost)
+    n_cpu, circ, picked = bench.cpu_plan("qft", 12, 0, 1e9)
+    assert n_cpu == 12 and len(picked) == len(W.qft(12).ops)
+
+
+def test_both_arms_print_the_same_config():
+    sys.path.insert(0, ROOT)
+    import bench
+    a = bench.workload_config("layers", 30, 20, 1)
+    assert a == bench.workload_config("layers", 30, 20, 1) and a["gates"] == 1490 and "30-qubit random" in a["workload"]
+    assert "sharded" in bench.workload_config("layers", 33, 8, 4)["workload"]

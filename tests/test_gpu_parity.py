@@ -96,7 +96,7 @@ def test_c1_random_layers(n, depth, backend):
     ref = _oracle(circ)
     assert maxabs(circ.run(backend=backend), ref) <= TOL
     circ.m[:]
-    shots = 1000 if n <= 16 else 200
+    shots = 1000
     random.seed(7)
     want = _oracle(circ, shots=shots)
     random.seed(7)
@@ -128,6 +128,103 @@ def test_c3_qaoa_energy(n, backend):
     want = O.expectation([(1.0, [("Z", i), ("Z", j)]) for i, j in edges], psi)
     assert abs(circ.run(backend=backend, hamiltonian=h) - want) < 1e-10
     assert maxabs(circ.run(backend=backend), psi) <= TOL
+
+
+def test_c3_qaoa_28_qubits_energy_against_the_statevector_route():
+    """BASELINE configs[2] at full size: run(hamiltonian=...) -- reductions on the device-resident state --
+    against the energy computed on the host from the downloaded statevector, term by term."""
+    from qaqarot_b200 import workloads as W
+    n = 28
+    circ, ham, edges = W.qaoa_maxcut(n)
+    be = B200Backend()
+    got = circ.run(backend=be, hamiltonian=ham)
+    psi = circ.run(backend=be)
+    prob = (psi.real ** 2 + psi.imag ** 2).reshape([2] * n)            # axis k = qubit n-1-k
+    del psi
+    assert abs(float(prob.sum()) - 1.0) < 1e-10
+    want = 0.0
+    for i, j in edges:
+        keep = (n - 1 - i, n - 1 - j)
+        m = prob.sum(axis=tuple(a for a in range(n) if a not in keep))
+        want += float(m[0, 0] + m[1, 1] - m[0, 1] - m[1, 0])
+    be.close()
+    assert abs(got - want) < 1e-10
+
+
+def test_readme_hamiltonian_example(backend):
+    """/root/reference/README.md:83-89: Circuit(4).x[:].run(hamiltonian=Z[0] + Z[1]) == -2.0."""
+    assert Circuit(4).x[:].run(backend=backend, hamiltonian=1 * Z[0] + 1 * Z[1]) == -2.0
+
+
+def test_ignore_global_phase(backend):
+    """utils.ignore_global_phase (utils.py:130-144) on the device: k_first_above + k_scale."""
+    rng = np.random.default_rng(3)
+    for n in (1, 4, 11, 16):
+        case = {"name": "ig", "n": n, "ops": C.random_ops(rng, n, 30 + 2 * n, True), "initial_seed": None,
+                "run": {"shots": None, "seed": None, "returns": None}}
+        circ = C.build(Circuit, case)
+        assert maxabs(circ.run(backend=backend, ignore_global=True), _oracle(circ, ignore_global=True)) <= TOL
+    v = Circuit().x[0].rz(1.0)[0].run(backend=backend, ignore_global=True)
+    assert np.allclose(v, [0, 1], atol=1e-15)
+    # the first amplitudes are (numerically) zero: the search has to pass them
+    circ = Circuit(12).x[11].h[0].rz(0.9)[11].cphase(0.3)[0, 11]
+    assert maxabs(circ.run(backend=backend, ignore_global=True), _oracle(circ, ignore_global=True)) <= TOL
+
+
+def test_cache_copy_and_append_on_the_device(backend):
+    """make_cache -> run -> append -> run, Circuit.copy() with its backend, oneshot (numpy_backend.py:564-568,
+    610-685; backendbase.py:27-33; tests/test_circuit.py test_cache_then_append) on device snapshots."""
+    be = backend.copy()
+    n = 10
+    c = Circuit(n).h[:].rz(0.4)[3].cx[3, 9].cx[0, 5].m[:]
+    c._backends["b200"] = be
+    assert be.cache is None and be.cache_idx == -1
+    c.make_cache(backend="b200")
+    assert be.cache is not None and be.cache_idx == len(c.ops) - 2
+    random.seed(3)
+    want = _oracle(c, shots=100)
+    random.seed(3)
+    assert c.run(backend="b200", shots=100) == want
+    c.x[1].h[2].m[1]
+    random.seed(4)
+    want = _oracle(c, shots=50)
+    random.seed(4)
+    assert c.run(backend="b200", shots=50) == want and be.cache is not None
+    c2 = c.copy()
+    be2 = c2._backends["b200"]
+    assert be2 is not be and be2.cache is not None and be2.cache is not be.cache
+    random.seed(5)
+    want = _oracle(c2, shots=30)
+    random.seed(5)
+    assert c2.run(backend="b200", shots=30) == want
+    random.seed(6)
+    wsv, wkey = O.OracleBackend().oneshot(c.ops, n) if hasattr(O.OracleBackend, "oneshot") else (None, None)
+    if wsv is not None:
+        random.seed(6)
+        gsv, gkey = c.oneshot(backend="b200")
+        assert gkey == wkey and maxabs(gsv, wsv) <= TOL
+    d = Circuit().x[0].m[0]                                   # a different qubit count invalidates the snapshot
+    d._backends["b200"] = be
+    assert d.run(backend="b200", shots=3) == Counter({"1": 3}) and be.cache is None
+    be.close()
+    be2.close()
+
+
+@pytest.mark.parametrize("name", ["c1", "qft", "qaoa", "random"])
+def test_fused_circuit_from_the_transpiler_backend_runs_on_the_device(name, backend):
+    """run(backend="b200_fuse") returns the planner's normal form as a circuit (transpile.py): executed on the device it
+    gives the original circuit's statevector."""
+    n = 13
+    rng = np.random.default_rng(8)
+    ops = {"c1": lambda: C.random_layer_ops(n, 8), "qft": lambda: C.qft_ops(n, 4321), "qaoa": lambda: C.qaoa_ops(n - 1)[0],
+           "random": lambda: C.random_ops(rng, n, 120, True)}[name]()
+    nq = n - 1 if name == "qaoa" else n
+    circ = C.build(Circuit, {"name": name, "n": nq, "ops": ops})
+    fused = circ.run(backend="b200_fuse")
+    assert isinstance(fused, Circuit) and fused.n_qubits == circ.n_qubits
+    want = _oracle(circ)
+    assert maxabs(fused.run(backend=backend), want) <= TOL
+    assert maxabs(circ.run(backend=backend), want) <= TOL
 
 
 def test_midcircuit_and_reset_against_oracle(backend):

