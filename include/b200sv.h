@@ -144,6 +144,13 @@ int b200_ipc_close(void* peer_amps);
    amp[i with lbit = 1 - my_bit] <-> peer_amps[i with lbit = my_bit], by loads / stores over NVLink, synchronous.
    The two partners call it on disjoint pair ranges; the caller fences both processes before and after. */
 int b200_peer_swap(b200_state* st, void* peer_amps, int lbit, int my_bit, uint64_t start, uint64_t count);
+/* k local index bits `lbits` (ascending) exchanged with k global bits in ONE step: called once per partner shard (the
+   2^k - 1 shards that differ from this one in a subset of those global bits).  For the patterns i in [start, start +
+   count) of the 2^(n-k) index patterns without the k bits, amp[i | mine_pat] <-> peer_amps[i | peer_pat], where
+   mine_pat holds the partner's values of the global bits on the local bits and peer_pat this shard's.  Asynchronous on
+   the state's stream unless sync != 0; partners take disjoint ranges; the caller fences all processes before and after. */
+int b200_peer_swap_bits(b200_state* st, void* peer_amps, const int32_t* lbits, int k, uint64_t mine_pat, uint64_t peer_pat,
+                        uint64_t start, uint64_t count, int sync);
 
 /* ---- measurement support for bench.py / profiling ------------------------------------------------ */
 

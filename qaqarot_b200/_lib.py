@@ -75,6 +75,8 @@ _SIGNATURES = {
     "b200_ipc_open": (C.c_int, [C.c_int, C.c_void_p, _P(C.c_void_p)]),
     "b200_ipc_close": (C.c_int, [C.c_void_p]),
     "b200_peer_swap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64]),
+    "b200_peer_swap_bits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64,
+                                      C.c_uint64, C.c_int]),
     "b200_event_record": (C.c_int, [C.c_void_p, C.c_int]),
     "b200_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _P(C.c_double)]),
     "b200_host_alloc": (C.c_int, [C.c_size_t, _P(C.c_void_p)]),

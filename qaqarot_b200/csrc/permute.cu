@@ -196,9 +196,69 @@ __global__ void __launch_bounds__(256) k_peer_swap(c128* __restrict__ mine, c128
   }
 }
 
+// The same for k local bits at once (a remap of k global wires in one step, SURVEY 8e "general k: all-to-all"): with
+// the partner that differs from this shard in a subset d of the k global bits, the block of this shard whose local
+// bits equal the PARTNER's global bits (`mine_pat`) trades places with the partner's block whose local bits equal
+// THIS shard's global bits (`peer_pat`), all other bits equal.  One call per partner, 2^k - 1 partners, each block
+// 2^(n-k) amplitudes: (1 - 2^-k) of the shard leaves, against k / 2 for k single-bit exchanges.
+__global__ void __launch_bounds__(256) k_peer_swap_bits(c128* __restrict__ mine, c128* __restrict__ peer, uint64_t start,
+                                                        uint64_t count, BitPositions bp, uint64_t mine_pat,
+                                                        uint64_t peer_pat) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < count; i += 4 * stride) {
+    c128 x[4], y[4];
+    uint64_t k0[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) k0[k] = spread(start + i + k * stride, bp);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) y[k] = __ldcg(peer + (k0[k] | peer_pat));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x[k] = __ldcg(mine + (k0[k] | mine_pat));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) __stcg(peer + (k0[k] | peer_pat), x[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) __stcg(mine + (k0[k] | mine_pat), y[k]);
+  }
+  for (; i < count; i += stride) {
+    const uint64_t k0 = spread(start + i, bp);
+    const c128 y = __ldcg(peer + (k0 | peer_pat)), x = __ldcg(mine + (k0 | mine_pat));
+    __stcg(peer + (k0 | peer_pat), x);
+    __stcg(mine + (k0 | mine_pat), y);
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_peer_swap_bits(b200_state* st, void* peer_amps, const int32_t* lbits, int k, uint64_t mine_pat,
+                                   uint64_t peer_pat, uint64_t start, uint64_t count, int sync) {
+  B200_REQUIRE(st != nullptr && (peer_amps != nullptr || count == 0) && lbits != nullptr, "b200_peer_swap_bits: null argument");
+  B200_REQUIRE(k >= 1 && k <= 8 && k <= st->n, "b200_peer_swap_bits: 1..8 local bits");
+  BitPositions bp;
+  bp.n = k;
+  uint64_t mask = 0;
+  for (int j = 0; j < k; ++j) {
+    B200_REQUIRE(lbits[j] >= 0 && lbits[j] < st->n && (j == 0 || lbits[j] > lbits[j - 1]),
+                 "b200_peer_swap_bits: local bits must be ascending and inside the shard");
+    bp.pos[j] = lbits[j];
+    mask |= 1ull << lbits[j];
+  }
+  B200_REQUIRE((mine_pat & ~mask) == 0 && (peer_pat & ~mask) == 0 && mine_pat != peer_pat,
+               "b200_peer_swap_bits: the two block patterns must differ and lie on the local bits");
+  const uint64_t block = st->dim >> k;
+  B200_REQUIRE(start <= block && count <= block - start, "b200_peer_swap_bits: range exceeds the block");
+  B200_CUDA(cudaSetDevice(st->device));
+  if (count) {
+    k_peer_swap_bits<<<kSMs * 8, 256, 0, st->stream>>>(st->amp, static_cast<c128*>(peer_amps), start, count, bp, mine_pat,
+                                                       peer_pat);
+    st->launches++;
+    B200_CUDA(cudaGetLastError());
+  }
+  if (sync) B200_CUDA(cudaStreamSynchronize(st->stream));
+  return 0;
+}
 
 extern "C" int b200_state_ipc_export(const b200_state* st, unsigned char* handle64) {
   B200_REQUIRE(st != nullptr && handle64 != nullptr, "b200_state_ipc_export: null argument");

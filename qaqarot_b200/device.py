@@ -178,6 +178,13 @@ class DeviceState:
     def ipc_close(self, peer_ptr: int) -> None:
         _lib.check(self._lib.b200_ipc_close(C.c_void_p(peer_ptr)))
 
+    def peer_swap_bits(self, peer_ptr: int, lbits: Sequence[int], mine_pat: int, peer_pat: int, start: int, count: int,
+                       sync: bool = False) -> None:
+        """One partner's share of a k-bit remap (include/b200sv.h: b200_peer_swap_bits)."""
+        lb = np.ascontiguousarray(lbits, dtype=np.int32)
+        _lib.check(self._lib.b200_peer_swap_bits(self._h, C.c_void_p(peer_ptr), lb.ctypes.data_as(C.c_void_p), int(lb.size),
+                                                 mine_pat, peer_pat, start, count, int(sync)))
+
     def peer_swap(self, peer_ptr: int, lbit: int, my_bit: int, start: int, count: int) -> None:
         """Pairs [start, start + count): amp[i | lbit = 1 - my_bit] <-> peer[i | lbit = my_bit] (synchronous)."""
         _lib.check(self._lib.b200_peer_swap(self._h, C.c_void_p(peer_ptr), lbit, my_bit, start, count))

@@ -525,11 +525,20 @@ def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = 
 
     for i_prim, p in enumerate(prims):
         if p.kind == "exchange":                  # from shard_schedule: wire p.target comes home, p.aux leaves
-            gpos, lbit = pos[p.target], pos[p.aux]
-            settle(lbit)                      # a non-diagonal 2x2 must be applied while its wire is local
-            push(Item("exchange", t=lbit, aux=gpos, n_prims=0))
-            move(lbit, gpos)
-            out.n_exchanges += 1
+            if i_prim > 0 and prims[i_prim - 1].kind == "exchange":
+                continue                          # (handled with the first exchange of its run)
+            run = []
+            while i_prim + len(run) < len(prims) and prims[i_prim + len(run)].kind == "exchange":
+                run.append(prims[i_prim + len(run)])
+            # a non-diagonal 2x2 must be applied while its wire is local: settle EVERY leaving wire first, so that the
+            # exchanges of the run stay adjacent and the sharded state executes them as one remap (exchange_many)
+            for e in run:
+                settle(pos[e.aux])
+            for e in run:
+                gpos, lbit = pos[e.target], pos[e.aux]
+                push(Item("exchange", t=lbit, aux=gpos, n_prims=0))
+                move(lbit, gpos)
+                out.n_exchanges += 1
             continue
         out.n_prims += 1
         if p.kind == "swap":

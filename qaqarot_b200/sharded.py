@@ -133,7 +133,8 @@ class ShardedState:
         self._bounce = None
         self.exchange_bytes = 0          # bytes this rank has sent (= received) in exchanges
         self.exchange_ms = 0.0           # wall time spent in exchanges (synchronised), for reporting
-        self.n_exchanges = 0
+        self.n_exchanges = 0             # global wires brought home
+        self.n_remaps = 0                # ... in this many steps of two barriers each (exchange_many)
         self.profile = None              # list of (kinds, ms) per executed segment while profiling is on
         self.use_p2p = True              # exchanges by the in-place peer-to-peer kernel (GPUs only)
 
@@ -341,14 +342,25 @@ class ShardedState:
             return
         if program.initial_pos and list(program.initial_pos) != self.layout:
             raise ValueError("program was planned for a different wire layout than the state is in")
-        for k, seg in enumerate(program.segments()):
+        segs = program.segments()
+        k = 0
+        while k < len(segs):
+            seg = segs[k]
             if isinstance(seg, Program):
                 self.st.apply(seg, init_basis=init_basis if k == 0 else None)
                 if self.profile is not None:
                     ms, kinds = self.st.last_op_times()
                     self.profile.append((kinds.copy(), ms.copy()))
-            else:
-                self.exchange(*seg)
+                k += 1
+                continue
+            # consecutive exchanges on distinct bits are ONE remap of several global wires
+            run = [seg]
+            while (k + len(run) < len(segs) and not isinstance(segs[k + len(run)], Program)
+                   and segs[k + len(run)][0] not in [l for l, _ in run] and segs[k + len(run)][1] not in [g for _, g in run]
+                   and len(run) < 8):
+                run.append(segs[k + len(run)])
+            self.exchange_many(run)
+            k += len(run)
         if program.final_pos:
             self.layout = list(program.final_pos)
 
@@ -387,6 +399,65 @@ class ShardedState:
         self.exchange_ms += (time.perf_counter() - t0) * 1e3
         self.exchange_bytes += 16 * half
         self.n_exchanges += 1
+        self.n_remaps += 1
+
+    def exchange_many(self, pairs: Sequence[Tuple[int, int]]) -> None:
+        """Swap k local index bits with k global bits in one step, pairs = [(local bit, global bit), ...] all distinct:
+        the amplitude at (shard G, local bits L) moves to (shard L, local bits G).  Each rank trades one block of
+        2^(n_local - k) amplitudes with each of the 2^k - 1 ranks that differ from it in a subset of those global bits,
+        so (1 - 2^-k) of the shard leaves -- k single exchanges would move k / 2 of it, behind 2k barriers instead of 2.
+        GPUs: one k_peer_swap_bits launch per partner, in place over CUDA-IPC peer memory.  Host stand-in (gloo tests):
+        the same blocks by send/recv.  NCCL without peer access: the single-bit exchanges one after the other."""
+        torch, dist = _torch()
+        import time
+        pairs = [(int(l), int(g)) for l, g in pairs]
+        if len(pairs) == 1:
+            return self.exchange(*pairs[0])
+        p2p = self.use_p2p and isinstance(self.local, _CudaLocal)
+        if not p2p and not isinstance(self.local, _HostLocal):
+            for l, g in pairs:
+                self.exchange(l, g)
+            return
+        pairs.sort()
+        k = len(pairs)
+        lbits, gposs = [l for l, _ in pairs], [g for _, g in pairs]
+        assert len(set(lbits)) == k and len(set(gposs)) == k and all(0 <= l < self.n_local <= g < self.n_qubits for l, g in pairs)
+        mine_g = [self._my_bit(g) for g in gposs]
+
+        def pattern(bits):
+            return sum(b << l for b, l in zip(bits, lbits))
+        block = 1 << (self.n_local - k)
+        self.local.before_comm()
+        dist.barrier(group=self.group)                          # every shard is quiescent
+        t0 = time.perf_counter()
+        for d in range(1, 1 << k):
+            diff = [(d >> j) & 1 for j in range(k)]
+            partner = self.rank ^ sum(diff[j] << (gposs[j] - self.n_local) for j in range(k))
+            mine_pat, peer_pat = pattern([a ^ b for a, b in zip(mine_g, diff)]), pattern(mine_g)
+            if p2p:
+                lo, cnt = (0, block // 2) if self.rank < partner else (block // 2, block - block // 2)
+                self.st.peer_swap_bits(self._peer_pointer(partner, any_partner=True), lbits, mine_pat, peer_pat, lo, cnt)
+            else:
+                psi = self.local.state.psi
+                idx = np.arange(block, dtype=np.int64)
+                for l in lbits:                                   # insert a zero at every exchanged bit (ascending)
+                    idx = ((idx >> l) << (l + 1)) | (idx & ((1 << l) - 1))
+                idx |= mine_pat
+                out = torch.from_numpy(psi[idx].view(np.float64).copy())
+                inc = torch.empty_like(out)
+                ops = [dist.P2POp(dist.isend, out, partner, self.group), dist.P2POp(dist.irecv, inc, partner, self.group)]
+                if self.rank > partner:
+                    ops.reverse()
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+                psi[idx] = inc.numpy().view(np.complex128)
+        self.local.before_comm()                                # the swaps were queued on the state's stream
+        self.local.after_comm()
+        dist.barrier(group=self.group)
+        self.exchange_ms += (time.perf_counter() - t0) * 1e3
+        self.exchange_bytes += 16 * block * ((1 << k) - 1)
+        self.n_exchanges += k
+        self.n_remaps += 1
 
     def _local_transpose(self, a: int, b: int) -> None:
         prog = Program()
@@ -395,14 +466,16 @@ class ShardedState:
         self.st.apply(prog)
         self.local.before_comm()
 
-    def _peer_pointer(self, partner: int) -> int:
+    def _peer_pointer(self, partner: int, any_partner: bool = False) -> int:
+        """The partner's shard mapped into this process (CUDA IPC).  The handles are published once, collectively (every
+        rank reaches its first exchange at the same point of the program) and every other shard of the box is mapped:
+        a remap of several global wires pairs this rank with ranks that differ in more than one bit."""
         torch, dist = _torch()
-        if partner not in self.local.peers:
-            # every rank publishes its handle once; all ranks take part in the gather
+        if not self.local.peers:
             handles = [None] * self.world
             dist.all_gather_object(handles, self.st.ipc_export(), group=self.group)
             for r, h in enumerate(handles):
-                if r != self.rank and r not in self.local.peers and bin(r ^ self.rank).count("1") == 1:
+                if r != self.rank:
                     self.local.peers[r] = self.st.ipc_open(h)
         return self.local.peers[partner]
 

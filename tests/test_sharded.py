@@ -57,6 +57,26 @@ def _worker(rank, world, port, errors):
             got = circ.run(backend=be, **kw)
             assert np.abs(got - oracle(circ, **kw)).max() <= 1e-12, f"statevector case {k}"
             assert be._compiled.prefix.n_exchanges > 0 or k == 2
+        if world >= 4:
+            st = be._work
+            assert st.n_remaps < st.n_exchanges, "several global wires never came home in one remap"
+            # ... and a remap of k bits is the k single-bit exchanges, in any order
+            vec = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
+            g = st.n_global
+            pairs = [(1, st.n_local + j) for j in range(g)]
+            pairs = [(st.n_local - 1 - 2 * j, st.n_local + j) for j in range(g)]
+            st.upload(vec)
+            st.exchange_many(pairs)
+            merged = st.download_shard().copy()
+            st.upload(vec)
+            for l, gp in reversed(pairs):
+                st.exchange(l, gp)
+            assert np.array_equal(st.download_shard(), merged)
+            want = vec.reshape([2] * n)
+            for l, gp in pairs:
+                want = np.swapaxes(want, n - 1 - l, n - 1 - gp)
+            lo = rank << st.n_local
+            assert np.array_equal(want.reshape(-1)[lo:lo + (1 << st.n_local)], merged)
         # 2. shots with the same seeded draws, measured in scrambled order, on global and local wires
         circ = C.build(Circuit, {"n": n, "ops": C.random_ops(rng, n, 60, False)}).m[(8, 2, 7, 0, 5)]
         random.seed(3)
