@@ -327,6 +327,7 @@ int b200_state_destroy(b200_state* st) {
   if (st->stream) cudaStreamSynchronize(st->stream);
   if (st->owns && st->amp) cudaFree(st->amp);
   if (st->d_partial) cudaFree(st->d_partial);
+  if (st->d_samp) cudaFree(st->d_samp);
   if (st->d_result) cudaFree(st->d_result);
   if (st->h_result) cudaFreeHost(st->h_result);
   if (st->d_words) cudaFree(st->d_words);

@@ -40,6 +40,8 @@ struct b200_state {
   std::vector<int32_t> op_kinds;
   uint64_t launches = 0;
   cudaEvent_t user_events[16] = {};
+  // grow-only scratch of the sampler's reductions (sample.cu): group bits, per-block partials, per-group sums
+  void* d_samp = nullptr;      size_t cap_samp = 0;
 };
 
 namespace b200 {

@@ -43,9 +43,12 @@ k_cond_prob(const c128* __restrict__ amp, uint64_t count, FreeRuns fr, const uin
   const uint64_t stride = (uint64_t)bx * blockDim.x;
   for (uint64_t k = (uint64_t)b * blockDim.x + threadIdx.x; k < count; k += stride) {
     const uint64_t i = deposit(k, fr) | fixed;
-    const c128 a0 = amp[i], a1 = amp[i | tbit];
+    const c128 a0 = amp[i];
     s0 += a0.x * a0.x + a0.y * a0.y;
-    s1 += a1.x * a1.x + a1.y * a1.y;
+    if (tbit) {                      // (no target qubit: S0 is the whole group and S1 stays 0)
+      const c128 a1 = amp[i | tbit];
+      s1 += a1.x * a1.x + a1.y * a1.y;
+    }
   }
   __shared__ double sh0[kSampThreads / 32], sh1[kSampThreads / 32];
 #pragma unroll
@@ -76,10 +79,25 @@ __global__ void k_group_finish(const double* __restrict__ partial, int n_groups,
   out[2 * (size_t)g + 1] = t1;
 }
 
-struct DeviceBuf {
-  void* p = nullptr;
-  ~DeviceBuf() { if (p) cudaFree(p); }
-};
+// The three device arrays of one reduction live in one grow-only allocation owned by the state (a descent makes up
+// to 64 reductions; allocating and freeing per level cost three cudaMalloc / cudaFree pairs each, and cudaFree
+// synchronises the device).
+static int sampler_scratch(b200_state* st, size_t bytes, unsigned char** out) {
+  if (bytes > st->cap_samp) {
+    if (st->d_samp) {
+      B200_CUDA(cudaStreamSynchronize(st->stream));
+      B200_CUDA(cudaFree(st->d_samp));
+      st->d_samp = nullptr;
+      st->cap_samp = 0;
+    }
+    size_t cap = 1 << 20;
+    while (cap < bytes) cap <<= 1;
+    B200_CUDA(cudaMalloc(&st->d_samp, cap));
+    st->cap_samp = cap;
+  }
+  *out = static_cast<unsigned char*>(st->d_samp);
+  return 0;
+}
 
 }  // namespace b200
 
@@ -92,10 +110,11 @@ static int cond_probs(b200_state* st, uint64_t fixed_mask, int qubit, const uint
                       double* sums) {
   const int max_blocks = kSMs * 16;
   const uint64_t tbit = qubit >= 0 ? 1ull << qubit : 0ull;
-  DeviceBuf d_bits, d_partial, d_out;
-  B200_CUDA(cudaMalloc(&d_bits.p, sizeof(uint64_t) * n_groups));
-  B200_CUDA(cudaMalloc(&d_partial.p, sizeof(double) * 2 * ((size_t)n_groups + (size_t)max_blocks)));
-  B200_CUDA(cudaMalloc(&d_out.p, sizeof(double) * 2 * n_groups));
+  const size_t sz_bits = sizeof(uint64_t) * (size_t)n_groups, sz_out = sizeof(double) * 2 * (size_t)n_groups;
+  const size_t sz_partial = sizeof(double) * 2 * ((size_t)n_groups + (size_t)max_blocks);
+  unsigned char* base = nullptr;
+  if (sampler_scratch(st, sz_bits + sz_out + sz_partial, &base)) return 1;
+  struct { void* p; } d_bits{base}, d_out{base + sz_bits}, d_partial{base + sz_bits + sz_out};
   FreeRuns fr;
   fr.n = 0;
   int free_bits = 0;

@@ -534,9 +534,14 @@ def normalize(prims: Sequence[Prim], n: int, fuse_1q: bool = True, fans: bool = 
             # exchanges of the run stay adjacent and the sharded state executes them as one remap (exchange_many)
             for e in run:
                 settle(pos[e.aux])
+            first_ex = None
             for e in run:
                 gpos, lbit = pos[e.target], pos[e.aux]
-                push(Item("exchange", t=lbit, aux=gpos, n_prims=0))
+                it = Item("exchange", t=lbit, aux=gpos, n_prims=0)
+                # (one major position for the whole run: an item placed "as early as its bits allow" lands behind the
+                # run, not between two of its exchanges)
+                push(it, None if first_ex is None else first_ex.pos)
+                first_ex = first_ex or it
                 move(lbit, gpos)
                 out.n_exchanges += 1
             continue
