@@ -516,9 +516,13 @@ def run_sharded(args, world: int):
     from qaqarot_b200 import ShardedB200Backend
     rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    # stdout carries exactly one JSON line; NCCL's own log (INFO: communicator, ranks, transports) goes to stderr
-    os.environ["NCCL_DEBUG"] = os.environ.get("B200_NCCL_DEBUG", os.environ.get("NCCL_DEBUG", "INFO"))
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly one JSON line: everything else written to file descriptor 1 from here on (NCCL prints its
+    # version banner with printf) lands on stderr, where NCCL's own log (INFO: communicator, ranks, transports) goes too
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    os.environ["NCCL_DEBUG"] = os.environ.get("B200_NCCL_DEBUG", "INFO")
+    os.environ.pop("NCCL_DEBUG_FILE", None)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     wname, n, depth = sharded_workload(args, world)
     circ, wl = build_workload(wname, n, depth)
@@ -530,7 +534,7 @@ def run_sharded(args, world: int):
     parity = sharded_parity_check(be, rank)
     if not parity["ok"]:
         if rank == 0:
-            print(json.dumps({"error": "sharded parity check failed", "check": parity}), flush=True)
+            os.write(json_fd, (json.dumps({"error": "sharded parity check failed", "check": parity}) + "\n").encode())
         dist.barrier()
         dist.destroy_process_group()
         raise SystemExit(1)
@@ -624,7 +628,7 @@ def run_sharded(args, world: int):
             "roofline": roofline, "exchange": exchange, "cpu_baseline": None, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks, "check": dict(parity, norm2=norm2),
         }
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     dist.barrier()
     dist.destroy_process_group()
 

@@ -107,10 +107,28 @@ class _Compiled:
         self.terminal = bool(self.rest) and all(isinstance(r, Prim) and r.kind == "measure" for r in self.rest)
 
     def matches(self, gates: Sequence, n_qubits: int, start: int, initial_layout=None, from_zero=False) -> bool:
+        """The cached plan serves a gate list that is the same BY VALUE (operation kind, targets, parameters, options):
+        an ansatz rebuilt with the angles it already had (vqe.py:67-83 builds a fresh circuit per call, once for the
+        sampler and again for the energies) does not re-plan.  New angles do: the plan's tables are functions of them."""
         return (n_qubits == self.n_qubits and start == self.start and len(gates) == len(self.gates)
                 and from_zero == self.from_zero
                 and (list(initial_layout) if initial_layout is not None else None) == self.initial_layout
-                and all(a is b for a, b in zip(gates, self.gates)))
+                and all(a is b or _same_op(a, b) for a, b in zip(gates, self.gates)))
+
+
+def _same_op(a, b) -> bool:
+    if type(a) is not type(b) or getattr(a, "lowername", None) != getattr(b, "lowername", None):
+        return False
+    try:
+        if a.targets != b.targets or len(a.params) != len(b.params):
+            return False
+        if not all(type(x) is type(y) and bool(np.all(x == y)) for x, y in zip(a.params, b.params)):
+            return False
+        return (getattr(a, "options", None) == getattr(b, "options", None)
+                and getattr(a, "key", None) == getattr(b, "key", None)
+                and getattr(a, "duplicated", None) == getattr(b, "duplicated", None))
+    except Exception:
+        return False
 
 
 def _check_initial(initial, n_qubits: int) -> np.ndarray:

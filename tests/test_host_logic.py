@@ -170,3 +170,28 @@ def test_blueqat_objects_are_accepted():
     from blueqat import vqe
     ref_e = vqe.sparse_expectation(h.to_expr().simplify().to_matrix(3, sparse="csc"), c2.run(backend="numpy"))
     assert abs(c2.run(backend=be, hamiltonian=h) - ref_e) < 1e-12
+
+
+def test_plan_cache_is_keyed_on_gate_values():
+    """A circuit rebuilt with the same angles (vqe.py:67-83 builds one per objective call) reuses the plan; a changed
+    angle, target or measurement key plans again and gives the new circuit's result."""
+    from qaqarot_b200 import workloads as W
+    be = cpu_backend()
+    a, _, _ = W.qaoa_maxcut(8, seed=3)
+    b, _, _ = W.qaoa_maxcut(8, seed=3)
+    c, _, _ = W.qaoa_maxcut(8, seed=4)
+    assert all(x is not y for x, y in zip(a.ops, b.ops))
+    va = a.run(backend=be)
+    plan_a = be._compiled
+    vb = b.run(backend=be)
+    assert be._compiled is plan_a and np.array_equal(va, vb)
+    vc = c.run(backend=be)
+    assert be._compiled is not plan_a
+    from oracle import sv_oracle as O
+    assert np.abs(vc - O.OracleBackend().run(c.ops, 8)).max() <= 1e-12 and np.abs(vc - va).max() > 1e-3
+    d = Circuit(3).h[0].rz(0.25)[1].m[0]
+    e = Circuit(3).h[0].rz(0.25)[2].m[0]
+    d.run(backend=be, shots=2)
+    plan_d = be._compiled
+    e.run(backend=be, shots=2)
+    assert be._compiled is not plan_d
