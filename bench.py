@@ -296,6 +296,9 @@ def tile_roofline(prog, n_local: int, op_ms, total_ms: float, from_zero: bool, s
         if fp64["floor_ms_per_launch"] > hbm["floor_ms_per_launch"]:
             out.update({"bound": "fp64", "achieved": tfl, "peak": fpeak, "unit": "TFLOP/s", "frac": tfl / fpeak})
     out["hbm"] = hbm
+    if isinstance(stored_traffic, dict):      # per launch: read + write passes, and the write-only pass that starts from |0...0>
+        n_wo = 1 if (from_zero and dom == OP_TILE and nbytes) else 0
+        stored_traffic = ((len(nbytes) - n_wo) * stored_traffic["read_write"] + n_wo * stored_traffic["write_only"]) / max(len(nbytes), 1)
     out.update({"traffic": stored_traffic,
                 "traffic_source": "stored ncu figure (profiles/traffic.json), not measured in this run" if stored_traffic else None,
                 "kernel": KIND_NAMES.get(dom, str(dom)), "launches_timed": cnt, "avg_launch_ms": avg_ms,
