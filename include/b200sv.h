@@ -62,7 +62,7 @@ typedef struct b200_op {
 
 const char* b200_last_error(void);
 int b200_device_count(int* out);
-int b200_version(void);                 /* 101; bumped whenever the TILE descriptor format changes */
+int b200_version(void);                 /* 102; bumped whenever the TILE descriptor format changes */
 
 /* ---- state lifetime (replaces _NumPyBackendContext.__init__/prepare, numpy_backend.py:36-62) ---- */
 

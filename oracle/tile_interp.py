@@ -131,7 +131,7 @@ def run_tile_pass(psi: np.ndarray, n: int, words: np.ndarray, reals: np.ndarray,
                     psi[keep] *= fan_fixed[fid][keep]
             elif dk == D_TAB:
                 assert int(fm) == 0 and int(lm) == 0, "a table applies to every amplitude"
-                # table[rho][variant]; variant = up to three selector bits: reg mask bits 4..9 and 10..15, fan byte.
+                # table[variant][rho], variants 17 entries apart; variant = up to three selector bits: reg mask bits 4..9 and 10..15, fan byte.
                 # A selector < 48 is an index bit outside the tile, 48 + l the tile-local thread bit l, 63 none.
                 ps = [(int(rm) >> 4) & 63, (int(rm) >> 10) & 63, fid]
                 assert ps == sorted(ps, key=lambda p: p == 63), "used selector bits come first"
@@ -145,8 +145,8 @@ def run_tile_pass(psi: np.ndarray, n: int, words: np.ndarray, reals: np.ndarray,
                         assert p - 48 in order[r:], "a selector inside the tile must be a thread bit of the round"
                         bit = (local >> np.uint64(p - 48)) & np.uint64(1)
                     var |= bit << np.uint64(i)
-                tab = cplx(roff_d, (1 << r) << m)
-                psi *= tab[(rho.astype(np.int64) << m) | var.astype(np.int64)]
+                tab = cplx(roff_d, (17 << m) if m else (1 << r))
+                psi *= tab[var.astype(np.int64) * 17 + rho.astype(np.int64)]
             elif dk == D_PHASE:
                 assert tk == T_NONE
                 keep = cond & ((rho & rm) == rm)

@@ -14,7 +14,7 @@ from typing import List, Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libb200sv.so")
-ABI_VERSION = 101            # b200_version() of the library this planner's TILE descriptors are written for
+ABI_VERSION = 102            # b200_version() of the library this planner's TILE descriptors are written for
 SOURCES = ["b200sv.cu", "sample.cu", "tile.cu", "permute.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]

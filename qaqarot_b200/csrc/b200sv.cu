@@ -268,7 +268,7 @@ extern "C" {
 
 const char* b200_last_error(void) { return g_error.c_str(); }
 
-int b200_version(void) { return 101; }   // 101: TILE descriptors with layer / table records (tile.cu)
+int b200_version(void) { return 102; }   // 102: table variants 17 entries apart, [variant][rho] (tile.cu)
 
 int b200_device_count(int* out) {
   B200_REQUIRE(out != nullptr, "b200_device_count: null out");
@@ -542,7 +542,7 @@ int b200_apply_program(b200_state* st, const b200_op* ops, int n_ops, const uint
       }
     } else if (op.kind == B200_OP_TILE) {
       B200_REQUIRE(op.woff + (uint64_t)op.wlen <= n_words, "TILE descriptor out of range");
-      if (launch_tile_pass(st, st->d_words + op.woff, words + op.woff, op.wlen, st->d_reals, n_reals, pending_init))
+      if (launch_tile_pass(st, st->d_words + op.woff, words + op.woff, op.wlen, st->d_reals, reals, n_reals, pending_init))
         return 1;
       pending_init = kNoInit;
     } else if (op.kind == B200_OP_PERMUTE) {

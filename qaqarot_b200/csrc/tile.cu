@@ -61,7 +61,8 @@
 //                  3 = phase  amp *= reals[offset] where rho satisfies reg_mask (never fused with a target stage)
 //                  4 = fan without entries: amp *= reals[offset] on register bit j (a 1-qubit phase, no fan record)
 //                  5 = fan whose entries all lie outside the tile: amp *= fix[fan], no tables
-//                  6 = table: amp[rho] *= table[rho][variant] (2^R x 2^m complex), any diagonal on the register bits;
+//                  6 = table: amp[rho] *= table[variant][rho] (2^m tables of 2^R complex, 17 entries apart), any diagonal on
+//                      the register bits;
 //                      variant = selector bits p1 | p2 << 1 | p3 << 2 with p1 = reg_mask >> 4 & 63, p2 = reg_mask >> 10
 //                      & 63, p3 = fan byte; a selector < 48 is an index bit outside the tile, 48 + l the tile-local
 //                      thread bit l, 63 none (m = selectors in use, packed first) -- fans and phases whose other
@@ -83,35 +84,74 @@ constexpr int D_NONE = 0, D_FANT = 1, D_FAN = 2, D_PHASE = 3, D_W = 4, D_FIX = 5
 __host__ __device__ __forceinline__ uint32_t swz(uint32_t l) { return l ^ ((l >> 3) & 7u); }
 
 // ---- mbarrier / TMA primitives (PTX) -----------------------------------------------------------------------------
+// Everything that runs INSIDE the tile loop is a plain `asm` (not `asm volatile`) with a "memory" clobber and a dummy
+// result (always 0) that the caller ORs into a token which ends up in a shared-memory address.  The clobber keeps the
+// statement ordered against every load and store and forbids merging or hoisting it; the consumed result keeps it
+// alive.  Why not `asm volatile`: with a volatile asm (or a __syncthreads / __syncwarp / __shfl intrinsic) anywhere
+// inside a loop nest, NVVM + ptxas stop treating the loop counters of that nest as warp-uniform, and the record loop
+// below then reads its records and coefficients with per-thread LDC into vector registers instead of LDCU into
+// uniform registers (measured on tools/ur_probe.cu: 96 of 96 DFMA / DMUL take a UR operand without, 0 of 96 with).
 __device__ __forceinline__ uint32_t sptr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sptr(b)), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sptr(b)), "r"(bytes) : "memory");
+__device__ __forceinline__ uint32_t mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  uint32_t d;
+  asm("{\n\tmbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %2;\n\tmov.u32 %0, 0;\n\t}" : "=r"(d) : "r"(sptr(b)), "r"(bytes) : "memory");
+  return d;
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sptr(b)) : "memory");
+__device__ __forceinline__ uint32_t mbar_wait(uint64_t* b, uint32_t parity) {
+  uint32_t d;
+  asm("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\tmov.u32 %0, 0;\n\t}" : "=r"(d) : "r"(sptr(b)), "r"(parity) : "memory");
+  return d;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
-  asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-               "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(sptr(b)), "r"(parity) : "memory");
+__device__ __forceinline__ uint32_t tma_load5(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, const int (&c)[5]) {
+  uint32_t d;
+  asm("{\n\tcp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%1], [%2, {%4, %5, %6, %7, %8}], [%3];\n\t"
+      "mov.u32 %0, 0;\n\t}"
+      : "=r"(d) : "r"(sptr(smem_dst)), "l"(tm), "r"(sptr(bar)), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]) : "memory");
+  return d;
 }
-__device__ __forceinline__ void tma_load5(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, const int (&c)[5]) {
-  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-               ::"r"(sptr(smem_dst)), "l"(tm), "r"(sptr(bar)), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]) : "memory");
+__device__ __forceinline__ uint32_t tma_store5(const CUtensorMap* tm, const void* smem_src, const int (&c)[5]) {
+  uint32_t d;
+  asm("{\n\tcp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%1, {%3, %4, %5, %6, %7}], [%2];\n\tmov.u32 %0, 0;\n\t}"
+      : "=r"(d) : "l"(tm), "r"(sptr(smem_src)), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]) : "memory");
+  return d;
 }
-__device__ __forceinline__ void tma_store5(const CUtensorMap* tm, const void* smem_src, const int (&c)[5]) {
-  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
-               ::"l"(tm), "r"(sptr(smem_src)), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]) : "memory");
+__device__ __forceinline__ uint32_t bulk_commit() {
+  uint32_t d;
+  asm("{\n\tcp.async.bulk.commit_group;\n\tmov.u32 %0, 0;\n\t}" : "=r"(d) : : "memory");
+  return d;
 }
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ uint32_t bulk_wait_read() {
+  uint32_t d;
+  asm("{\n\tcp.async.bulk.wait_group.read %1;\n\tmov.u32 %0, 0;\n\t}" : "=r"(d) : "n"(N) : "memory");
+  return d;
+}
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint32_t fence_async() {
+  uint32_t d;
+  asm("{\n\tfence.proxy.async.shared::cta;\n\tmov.u32 %0, 0;\n\t}" : "=r"(d) : : "memory");
+  return d;
+}
+// A uniform value on its way into per-thread arithmetic goes through this opaque move first.  Without it ptxas gives
+// up the uniform register for the value AND for everything it was derived from (the loop counter it indexes with, the
+// record it was read from ...): one shared-memory address computed from the round number was enough to turn the whole
+// record loop back into per-thread code.
+__device__ __forceinline__ uint32_t vreg(uint32_t x) {
+  uint32_t y;
+  asm("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
 template <int NT>
-__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(NT) : "memory"); }
+__device__ __forceinline__ uint32_t group_sync(uint32_t g) {
+  uint32_t d;
+  asm("{\n\tbar.sync %1, %2;\n\tmov.u32 %0, 0;\n\t}" : "=r"(d) : "r"(1u + g), "n"(NT) : "memory");
+  return d;
+}
 
 __host__ __device__ constexpr int ctz_c(int i) { return (i & 1) ? 0 : (i & 2) ? 1 : (i & 4) ? 2 : (i & 8) ? 3 : 4; }
 
@@ -249,14 +289,14 @@ __device__ __forceinline__ void fan_apply(c128 (&v)[1 << R], c128 wt, const doub
 constexpr uint32_t kKeyLayer = 0xF0u, kKeyTab = 0xF1u;
 
 // (a0, a1) <- E(y) F(x) E(z) (a0, a1) on the pairs of register bit J, for the J in `mask`; payload 4 x (z, x, y, -).
-// y = 0 (two updates; the record's diag stage rescales) skips the third loop: a warp-uniform branch.
+// The third update runs for the J in `mask3` only (y != 0, found once per CTA when the records are decoded: a test of
+// the loaded y made every rotation wait for its payload before the first shear could issue).
 template <int R>
-__device__ __forceinline__ void layer_apply(c128 (&v)[1 << R], const double* __restrict__ pay, uint32_t mask) {
+__device__ __forceinline__ void layer_apply(c128 (&v)[1 << R], const double* __restrict__ pay, uint32_t mask, uint32_t mask3) {
 #pragma unroll
   for (int J = 0; J < R; ++J) {
     if (!((mask >> J) & 1u)) continue;
     const double2 zx = reinterpret_cast<const double2*>(pay)[2 * J];
-    const double y = pay[4 * J + 2];
 #pragma unroll
     for (int rho = 0; rho < (1 << R); ++rho) {
       if (rho & (1 << J)) continue;
@@ -266,7 +306,8 @@ __device__ __forceinline__ void layer_apply(c128 (&v)[1 << R], const double* __r
           "fma.rn.f64 %2, %5, %0, %2;\n\tfma.rn.f64 %3, %5, %1, %3;"
           : "+d"(a0.x), "+d"(a0.y), "+d"(a1.x), "+d"(a1.y) : "d"(zx.x), "d"(zx.y));
     }
-    if (y != 0.0) {
+    if ((mask3 >> J) & 1u) {
+      const double y = pay[4 * J + 2];
 #pragma unroll
       for (int rho = 0; rho < (1 << R); ++rho) {
         if (rho & (1 << J)) continue;
@@ -278,52 +319,88 @@ __device__ __forceinline__ void layer_apply(c128 (&v)[1 << R], const double* __r
     }
   }
 }
-// amp[rho] *= tab[rho * stride]: the table of this thread's variant (entries of one rho for all variants are adjacent,
-// so the threads of a warp that picked different variants read different banks)
+// amp[rho] *= tab[rho]: the table of this thread's variant.  Variants lie kTabPitch = 17 entries apart, so every load
+// has a compile-time offset from one base, and threads of a warp that picked different variants read different
+// 16-byte bank groups ((variant + rho) mod 8).
+constexpr uint32_t kTabPitch = 17;
 template <int R>
-__device__ __forceinline__ void tab_apply(c128 (&v)[1 << R], const double2* __restrict__ tab, uint32_t stride) {
+__device__ __forceinline__ void tab_apply(c128 (&v)[1 << R], const double2* __restrict__ tab) {
 #pragma unroll
   for (int rho = 0; rho < (1 << R); ++rho) {
-    const double2 f = tab[rho * stride];
+    const double2 f = tab[rho];
     amp_mul(v[rho], f.x, f.y, -f.y);
   }
 }
 
-template <int R>
-__device__ __forceinline__ void run_target(c128 (&v)[1 << R], uint32_t key1, uint32_t rm, const double* __restrict__ pay) {
-  switch (key1) {
-#define B200_T_CASES(J)                                                                           \
-    case 16 * J + T_MATC: mat_c<R, (J < R ? J : 0), false>(v, pay, 0); break;                       \
-    case 16 * J + T_MATR: mat_r<R, (J < R ? J : 0), false>(v, pay, 0); break;                       \
-    case 16 * J + T_X: perm_x<R, (J < R ? J : 0), false>(v, 0); break;                              \
-    case 16 * J + T_MATC + 8: mat_c<R, (J < R ? J : 0), true>(v, pay, rm); break;                   \
-    case 16 * J + T_MATR + 8: mat_r<R, (J < R ? J : 0), true>(v, pay, rm); break;                   \
-    case 16 * J + T_X + 8: perm_x<R, (J < R ? J : 0), true>(v, rm); break;
-    B200_T_CASES(0) B200_T_CASES(1) B200_T_CASES(2) B200_T_CASES(3)
-#undef B200_T_CASES
-    default: break;
+// Dispatch on (register bit, kind) by BIT TESTS on uniform values: never a `switch`, and never a chain of four or more
+// equality tests of one value either (the compiler turns that back into a switch) -- a jump table is an indirect branch
+// through a per-thread register, and the key it is computed from then stops being a uniform value.
+template <int R, int J>
+__device__ __forceinline__ void run_target_j(c128 (&v)[1 << R], uint32_t kind, uint32_t rm, const double* __restrict__ pay) {
+  // kind = T_MATC (1), T_MATR (2), T_X (3), + 8 with controls among the register bits
+  if (kind & 8u) {
+    if (!(kind & 2u)) mat_c<R, J, true>(v, pay, rm);
+    else if (!(kind & 1u)) mat_r<R, J, true>(v, pay, rm);
+    else perm_x<R, J, true>(v, rm);
+  } else {
+    if (!(kind & 2u)) mat_c<R, J, false>(v, pay, 0);
+    else if (!(kind & 1u)) mat_r<R, J, false>(v, pay, 0);
+    else perm_x<R, J, false>(v, 0);
   }
 }
-template <int R, int NWARP_T>
-__device__ __forceinline__ void run_diag(c128 (&v)[1 << R], uint32_t key2, uint32_t rm, const double* __restrict__ pay,
-                                         c128 wt) {
-  const double2* __restrict__ reg_t = reinterpret_cast<const double2*>(pay) + 32 + NWARP_T;
-  switch (key2) {
-#define B200_D_CASES(J)                                                                           \
-    case 8 * J + D_FANT: case 8 * J + D_W: case 8 * J + D_FIX:                                      \
-      fant_apply<R, (J < R ? J : R)>(v, wt); break;                                                 \
-    case 8 * J + D_FAN: fan_apply<R, (J < R ? J : R)>(v, wt, reg_t); break;
-    B200_D_CASES(0) B200_D_CASES(1) B200_D_CASES(2) B200_D_CASES(3) B200_D_CASES(4)
-#undef B200_D_CASES
-    case 8 * 4 + D_PHASE: {
-      const double wx = pay[0], wy = pay[1];
-#pragma unroll
-      for (int rho = 0; rho < (1 << R); ++rho)
-        if ((rho & rm) == rm) amp_mul(v[rho], wx, wy, -wy);
-      break;
-    }
-    default: break;
+template <int R>
+__device__ __forceinline__ void run_target(c128 (&v)[1 << R], uint32_t key1, uint32_t rm, const double* __restrict__ pay) {
+  const uint32_t kind = key1 & 15u;
+  if (key1 & 0x20u) {
+    if (key1 & 0x10u) run_target_j<R, (3 < R ? 3 : 0)>(v, kind, rm, pay);
+    else run_target_j<R, (2 < R ? 2 : 0)>(v, kind, rm, pay);
+  } else {
+    if (key1 & 0x10u) run_target_j<R, 1>(v, kind, rm, pay);
+    else run_target_j<R, 0>(v, kind, rm, pay);
   }
+}
+// A fan (per-thread factor wt, optionally times a factor per register amplitude) on the amplitudes with register bit j
+// set (j = 4: every amplitude)
+template <int R>
+__device__ __forceinline__ void run_fan(c128 (&v)[1 << R], uint32_t j, bool with_reg, c128 wt, const double2* __restrict__ reg_t) {
+#define B200_F_CASE(J)                                            \
+  {                                                               \
+    if (with_reg) fan_apply<R, (J < R ? J : R)>(v, wt, reg_t);    \
+    else fant_apply<R, (J < R ? J : R)>(v, wt);                   \
+  }
+  if (j & 4u) B200_F_CASE(4)
+  else if (j & 2u) {
+    if (j & 1u) B200_F_CASE(3) else B200_F_CASE(2)
+  } else {
+    if (j & 1u) B200_F_CASE(1) else B200_F_CASE(0)
+  }
+#undef B200_F_CASE
+}
+// The same for a factor that is the same for every thread (kind D_W: a 1-qubit phase), read from the constant bank
+template <int R>
+__device__ __forceinline__ void run_phase1(c128 (&v)[1 << R], uint32_t j, const double* __restrict__ pay) {
+  const double wx = pay[0], wy = pay[1];
+#define B200_F_CASE(J)                                            \
+  {                                                               \
+    _Pragma("unroll")                                             \
+    for (int rho = 0; rho < (1 << R); ++rho)                      \
+      if (J >= R || ((rho >> (J < R ? J : 0)) & 1)) amp_mul(v[rho], wx, wy, -wy);  \
+  }
+  if (j & 4u) B200_F_CASE(4)
+  else if (j & 2u) {
+    if (j & 1u) B200_F_CASE(3) else B200_F_CASE(2)
+  } else {
+    if (j & 1u) B200_F_CASE(1) else B200_F_CASE(0)
+  }
+#undef B200_F_CASE
+}
+// amp *= w on the amplitudes whose register bits satisfy rm (kind D_PHASE)
+template <int R>
+__device__ __forceinline__ void run_phase_mask(c128 (&v)[1 << R], uint32_t rm, const double* __restrict__ pay) {
+  const double wx = pay[0], wy = pay[1];
+#pragma unroll
+  for (int rho = 0; rho < (1 << R); ++rho)
+    if (((uint32_t)rho & rm) == rm) amp_mul(v[rho], wx, wy, -wy);
 }
 
 // ---- pre-decoded pass (built once per CTA in shared memory) ------------------------------------------------------
@@ -348,11 +425,42 @@ constexpr int kMaxFanWords = 512;  // fan directory + records of the pass's fans
 //                                      z = thread mask | reg mask<<16                w = fixed mask bits 0..31
 //   all: y = target payload | diag payload<<16 (complex units, relative to the pass's payload)
 
-struct RoundHdr {                  // 16 bytes
-  uint16_t n_gates, first;         // records [first, first + n_gates)
-  uint16_t srb[4];                 // slot XOR masks of the register bits: swz(1 << order[k])
+// What a record needs in PER-THREAD arithmetic (shared-memory addresses of per-thread tables, thread-bit masks, table
+// selectors) does not come from the uniform record: a uniform value that meets per-thread values in an address or a
+// shift makes the compiler drop the uniform register for it and for everything upstream (the record, the loop counter).
+// Those fields travel in a second stream of 32-bit words in shared memory, read through a per-thread cursor that runs
+// in step with the uniform record loop:
+// (4-word items start on a 16-byte boundary; the stream is padded in front of them)
+//   round:   4 words  srb01, srb23 (slot masks of the register bits, 16 bits each), byte offset of the round's `thr`
+//            row in TileSmem, 0
+//   LT record with table variants:  1 word   p1 | p2 << 6 | p3 << 12 | table offset (complex units) << 18
+//   LF record (fan kinds 1, 2, 5):  1 word   fan | table offset (complex units) << 8
+//   general record:                 4 words  thread mask | reg mask << 16, fixed mask bits 0..31,
+//                                            fixed mask bits 32..39 | fan << 8, diag payload offset (complex units)
+constexpr int kMaxVsWords = 8 * kMaxRounds + 4 * kMaxGates + 8;
+
+struct RoundConst {                // 32 bytes; 32-bit fields read as one uint4 (16-bit parameter loads are not uniform loads)
+  uint32_t ng_first;               // n_gates | first << 16: records [first, first + n_gates)
+  uint32_t srb01, srb23;           // slot XOR masks of the register bits, swz(1 << order[k]), 16 bits each
   uint32_t pad;
+  uint64_t o_lo, o_hi;             // order[0..16) of the round, 8 bits each
 };
+
+// Everything about the pass that is the same for every thread: a KERNEL PARAMETER (constant bank), decoded on the host
+// by launch_tile_pass.  The record loop and the gate payload are then read with uniform loads (LDCU) into uniform
+// registers: the dispatch runs on the uniform datapath with uniform branches (no BSSY / BSYNC pairs, no per-thread
+// decode), and rotation coefficients and table entries are UR operands of the DFMA / DMUL instructions -- no LDS, no
+// vector registers, no address arithmetic (round 2; before, half of a layer pass's warp time sat on shared-memory
+// scoreboards and dispatch branches, profiles/r02c_layers30_ncu_full.md).
+struct PassConst {
+  uint32_t n_rounds, n_fans, dir_off, rounds_off;
+  uint32_t pay_lo, pay_len, n_vs, pad1;
+  RoundConst rh[kMaxRounds];
+  uint4 rec[kMaxGates + 1];
+  uint32_t vs[kMaxVsWords];        // the per-thread side of the records (copied to shared memory), see below
+  double pay[kMaxPayload];         // the pass's matrices, phases, tables (the same range of `reals`)
+};
+static_assert(sizeof(PassConst) + 512 <= 32764, "kernel parameters are limited to 32 764 bytes");
 
 // How a tile maps to the tensor the TMA unit sees (kernel parameter, built by build_tile_map).
 struct TileMapDev {
@@ -368,12 +476,10 @@ struct TileSmem {
   c128 stage[kStages][1 << A];     // 1024-byte aligned (SWIZZLE_128B atoms): first member of the dynamic allocation
   c128 fix[kGroups][kMaxFans];     // per-tile fan products, one set per compute group
   uint64_t spread[kSpreadTabs][64];
-  uint4 rec[kMaxGates + 1];
-  double pay[kMaxPayload];         // the pass's matrices, phases and fan tables
+  double pay[kMaxPayload];         // copy of PassConst::pay for the reads indexed per thread (fan tables, table variants)
   uint64_t fanw[kMaxFanWords];     // fan directory and records (entry counts, payload offsets, fixed-bit masks)
-  RoundHdr rh[kMaxRounds];
+  alignas(16) uint32_t vs[kMaxVsWords];   // copy of PassConst::vs
   uint16_t thr[kMaxRounds][1 << (A - R)];   // per round, per thread: its local index bits
-  uint32_t round_off[kMaxRounds];
   uint64_t full[kStages][2];       // the tile's TMA load has landed; index = use of the stage & 1
 };
 
@@ -383,9 +489,9 @@ struct TileSmem {
 // record faster (round 1: 45.2 -> 41.0 ms on the 30-qubit QFT).
 template <int A, bool FULL, bool TIMING>
 __global__ void __launch_bounds__(kGroups * (1 << (A - R)), 1)
-k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMapDev tm, uint64_t n_tiles,
-       uint64_t index_offset, const uint64_t* __restrict__ desc, const double* __restrict__ reals, uint32_t flags,
-       uint64_t init_tile, uint32_t init_local, unsigned long long* __restrict__ phase_cycles) {
+k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMapDev tm, const __grid_constant__ PassConst P,
+       uint64_t n_tiles, uint64_t index_offset, const uint64_t* __restrict__ desc, const double* __restrict__ reals,
+       uint32_t flags, uint64_t init_tile, uint32_t init_local, unsigned long long* __restrict__ phase_cycles) {
   constexpr int NT = 1 << (A - R), PER = 1 << R, NTB = A - R;
   constexpr int NWARP_T = (NTB > 5) ? (1 << (NTB - 5)) : 1;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -393,10 +499,9 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
 
   uint32_t tid;                    // (volatile: ptxas otherwise re-reads SR_TID.X inside the record loop)
   asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
-  const uint64_t h0 = desc[0], tb_lo = desc[1], tb_hi = desc[2];
-  const int n_rounds = (int)((h0 >> 24) & 0xFF), n_fans = (int)((h0 >> 32) & 0xFF);
-  const uint32_t dir_off = (uint32_t)(desc[3] & 0xFFFFFFFFu), rounds_off = (uint32_t)(desc[3] >> 32);
-  const uint32_t pay_lo = (uint32_t)(desc[4] & 0xFFFFFFFFu), pay_len = (uint32_t)(desc[4] >> 32);
+  const uint64_t tb_lo = desc[1], tb_hi = desc[2];
+  const int n_rounds = (int)P.n_rounds, n_fans = (int)P.n_fans;
+  const uint32_t dir_off = P.dir_off, rounds_off = P.rounds_off, pay_lo = P.pay_lo, pay_len = P.pay_len;
   // flags bit 1: the state is a basis vector that nobody has written yet -- every tile is all zeros except
   // tile `init_tile`, whose local index `init_local` holds 1 (B200_OP_INIT folded into this pass)
   const bool init = (flags & 2u) != 0;
@@ -404,15 +509,6 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
 
   // ---- one-time setup ---------------------------------------------------------------------------------------
   if (tid == 0) {
-    uint32_t pos = rounds_off, first = 0;
-    for (int rd = 0; rd < n_rounds; ++rd) {
-      const uint64_t rh = desc[pos];
-      S.round_off[rd] = pos;
-      S.rh[rd].n_gates = (uint16_t)(rh & 0xFFFF);
-      S.rh[rd].first = (uint16_t)first;
-      first += (uint32_t)(rh & 0xFFFF);
-      pos += (uint32_t)(rh >> 16);
-    }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&S.full[s][0], 1);
       mbar_init(&S.full[s][1], 1);
@@ -421,48 +517,18 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
   }
   for (uint32_t i = tid; i < pay_len; i += blockDim.x) S.pay[i] = reals[pay_lo + i];
   for (uint32_t i = dir_off + tid; i < rounds_off; i += blockDim.x) S.fanw[i - dir_off] = desc[i];
+  for (uint32_t i = tid; i < P.n_vs; i += blockDim.x) S.vs[i] = P.vs[i];
   for (uint32_t idx = tid; idx < kSpreadTabs * 64; idx += blockDim.x) {
     uint64_t x = (uint64_t)(idx & 63u) << (6 * (idx >> 6));
     for (int i = 0; i < A; ++i) x = insert_zero(x, byte_of(tb_lo, tb_hi, i));
     S.spread[idx >> 6][idx & 63u] = x;
   }
-  __syncthreads();
   for (int rd = 0; rd < n_rounds; ++rd) {
-    const uint64_t* __restrict__ rp = desc + S.round_off[rd];
-    const uint64_t o_lo = rp[1], o_hi = rp[2];
+    const uint64_t o_lo = P.rh[rd].o_lo, o_hi = P.rh[rd].o_hi;
     for (uint32_t t = tid; t < (uint32_t)NT; t += blockDim.x) {
       uint32_t lt = 0;
       for (int b = 0; b < NTB; ++b) lt |= ((t >> b) & 1u) << byte_of(o_lo, o_hi, R + b);
       S.thr[rd][t] = (uint16_t)lt;
-    }
-    if (tid < R) S.rh[rd].srb[tid] = (uint16_t)swz(1u << byte_of(o_lo, o_hi, tid));
-    const int ng = S.rh[rd].n_gates, first = S.rh[rd].first;
-    for (int gi = tid; gi < ng; gi += blockDim.x) {
-      const uint64_t g0 = rp[3 + 3 * gi], fm = rp[4 + 3 * gi], roffs = rp[5 + 3 * gi];
-      const uint32_t tk = (uint32_t)(g0 & 0xFF), j = (uint32_t)((g0 >> 8) & 0xFF), dk = (uint32_t)((g0 >> 16) & 0xFF);
-      const uint32_t fan = (uint32_t)((g0 >> 24) & 0xFF);
-      const uint32_t lm = (uint32_t)((g0 >> 32) & 0xFFFF), rm = (uint32_t)((g0 >> 48) & 0xFFFF);
-      const uint32_t pt = tk == T_NONE || tk == T_X ? 0u : (((uint32_t)roffs - pay_lo) >> 1);
-      const uint32_t pd = dk == D_NONE ? 0u : (((uint32_t)(roffs >> 32) - pay_lo) >> 1);
-      const uint32_t jj = j < (uint32_t)R ? j : 4u;            // 4 = no register target ("every amplitude")
-      const bool plain = lm == 0 && fm == 0 && (tk == T_NONE || tk == T_LAYER);
-      uint4 rec;
-      rec.y = pt | (pd << 16);
-      if (plain && (dk == D_NONE || dk == D_TAB)) {
-        rec.x = 1u | ((tk == T_LAYER ? rm & 15u : 0u) << 2) | (dk == D_TAB ? 0x100u : 0u);
-        rec.z = ((rm >> 4) & 63u) | (((rm >> 10) & 63u) << 8) | ((fan & 63u) << 16);
-        rec.w = 0;
-      } else if (plain && (dk == D_FANT || dk == D_FAN || dk == D_W || dk == D_FIX)) {
-        rec.x = 2u | ((tk == T_LAYER ? rm & 15u : 0u) << 2) | (jj << 6) | (dk << 9) | ((fan & 63u) << 12);
-        rec.z = rec.w = 0;
-      } else {
-        const uint32_t key1 = tk == T_NONE ? 0u : tk == T_LAYER ? kKeyLayer : 16u * jj + tk + (rm != 0 ? 8u : 0u);
-        const uint32_t key2 = dk == D_NONE ? 0u : dk == D_TAB ? kKeyTab : 8u * jj + dk;
-        rec.x = (key1 << 2) | (key2 << 10) | ((fan & 63u) << 18) | ((uint32_t)(fm >> 32) << 24);
-        rec.z = lm | (rm << 16);
-        rec.w = (uint32_t)fm;
-      }
-      S.rec[first + gi] = rec;
     }
   }
   __syncthreads();
@@ -483,9 +549,15 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
   };
 
   // ---- compute groups ----------------------------------------------------------------------------------------
-  const uint32_t g = tid / NT, t = tid % NT, lane = t & 31u, warp = t >> 5;
+  // The group number is the same for all threads of a warp; taken through a warp reduction it is a value the compiler
+  // KNOWS to be uniform (REDUX writes a uniform register), so the tile loop, the round loop and the record loop below
+  // are uniform control flow and may use the uniform datapath.
+  // (gv: the same number as a per-thread value, for addresses)
+  const uint32_t gv = tid / NT, g = __reduce_max_sync(0xFFFFFFFFu, gv), t = tid % NT, lane = t & 31u, warp = t >> 5;
   const uint32_t lane_off = lane << 4, warp_off = (32u + (NWARP_T > 1 ? warp : 0u)) << 4;      // into a fan's tables
-  c128* const fixp = S.fix[g];
+  c128* const fixp = S.fix[gv];
+  const unsigned char* const vsb = reinterpret_cast<const unsigned char*>(S.vs);
+  const unsigned char* const thrb = reinterpret_cast<const unsigned char*>(&S.thr[0][t]);
   unsigned char* const pay_b = reinterpret_cast<unsigned char*>(S.pay);
   // The sub-copies of a tile are issued by DIFFERENT warps of its group: a TMA instruction is a uniform-datapath
   // op, so the lanes of one warp that issue one each are served one after the other (~110 cycles per copy: with all
@@ -493,9 +565,10 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
   // waited at the barrier).  Thread (warp w, lane l) takes sub-copies l * NW + w, + NT, ...
   constexpr uint32_t NW = NT / 32;
   const int my_sub = (int)(lane * NW + warp);
+  uint32_t tok = 0;                // ORs the (zero) results of the synchronisation statements; see the primitives above
   // thread 0 of a group announces tile j of this CTA on its barrier ...
   auto expect = [&](uint32_t j) {
-    if (blockIdx.x + (uint64_t)j * gridDim.x < n_tiles) mbar_expect_tx(&S.full[j % kStages][(j / kStages) & 1u], 16u << A);
+    if (blockIdx.x + (uint64_t)j * gridDim.x < n_tiles) tok |= mbar_expect_tx(&S.full[j % kStages][(j / kStages) & 1u], 16u << A);
   };
   // ... and, after a barrier of the group, every thread requests its sub-copies into the tile's buffer
   auto request = [&](uint32_t j) {
@@ -507,21 +580,21 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
     for (int sub = my_sub; sub < n_sub; sub += NT) {
       int c[5];
       coords(base, sub, c);
-      tma_load5(S.stage[s] + (size_t)sub * tm.sub_amps, &tmap, fb, c);
+      tok |= tma_load5(S.stage[s] + (size_t)sub * tm.sub_amps, &tmap, fb, c);
     }
   };
   auto store_tile = [&](const c128* buf, uint64_t base) {
     for (int sub = my_sub; sub < n_sub; sub += NT) {
       int c[5];
       coords(base, sub, c);
-      tma_store5(&tmap, buf + (size_t)sub * tm.sub_amps, c);
+      tok |= tma_store5(&tmap, buf + (size_t)sub * tm.sub_amps, c);
     }
-    bulk_commit();
+    tok |= bulk_commit();
   };
   if (!init && g == 0) {            // prologue: the first three tiles
     if (t == 0)
       for (uint32_t j = 0; j < (uint32_t)kStages; ++j) expect(j);
-    group_sync<NT>(0);
+    tok |= group_sync<NT>(0);
     for (uint32_t j = 0; j < (uint32_t)kStages; ++j) request(j);
   }
   if (init) {
@@ -530,8 +603,8 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
     // bytes and computes one tile.
 #pragma unroll
     for (int i = 0; i < PER; ++i) S.stage[g][t + (uint32_t)i * NT] = make_double2(0.0, 0.0);
-    fence_async();
-    group_sync<NT>(g);
+    tok |= fence_async();
+    tok |= group_sync<NT>(g);
   }
   bool store_pending = false;       // this group's previous tile has been handed to the TMA unit, not yet waited for
   // B200_TILE_TIMING=1: thread 0 of every group accumulates the cycles it spends in each phase of a tile
@@ -548,7 +621,7 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
     if (tile >= n_tiles) break;
     if (init && tile != init_tile) {
       store_tile(S.stage[g], spread_tile(tile));
-      asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory");
+      tok |= bulk_wait_read<4>();
       tick(8);
       continue;
     }
@@ -556,26 +629,19 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
     const uint32_t s = init ? 2u : j % kStages, u = j / kStages;
     const uint64_t fixedidx = spread_tile(tile) | index_offset;
     const uint32_t fx_lo = (uint32_t)fixedidx, fx_hi = (uint32_t)(fixedidx >> 32);
-    // per-tile fixed-bit products of the fans, while the tile is still in flight (eight lanes per fan)
-    for (int f = (int)(4u * warp + (lane >> 3)); f < n_fans; f += (int)(4u * NW)) {
+    // per-tile fixed-bit products of the fans, while the tile is still in flight: one thread per fan (no warp shuffles
+    // inside the tile loop, see the note on the primitives; a pass has at most 64 fans of ~20 entries)
+    for (int f = (int)t; f < n_fans; f += NT) {
       const uint32_t off = (uint32_t)S.fanw[f] - dir_off;
       const uint64_t rec = S.fanw[off];
       const int ne = (int)(rec & 0xFFFFFFFFu);
       const double2* __restrict__ w = reinterpret_cast<const double2*>(S.pay + ((uint32_t)(rec >> 32) - pay_lo));
-      c128 p = make_double2(1.0, 0.0);
-      for (int e = (int)(lane & 7u); e < ne; e += 8) {
+      c128 p = w[0];
+      for (int e = 0; e < ne; ++e) {
         const uint64_t m = S.fanw[off + 1 + e];
         if ((fixedidx & m) == m) p = cmul(p, w[1 + e]);
       }
-      const uint32_t seg = 0xFFu << (lane & 24u);
-#pragma unroll
-      for (int o = 4; o > 0; o >>= 1) {
-        c128 q;
-        q.x = __shfl_xor_sync(seg, p.x, o);
-        q.y = __shfl_xor_sync(seg, p.y, o);
-        p = cmul(p, q);
-      }
-      if ((lane & 7u) == 0) fixp[f] = cmul(p, w[0]);
+      fixp[f] = p;
     }
     tick(0);                        // fan products
     // announce the tile that will use the previous tile's buffer next (j + 1, for the OTHER group); its sub-copies are
@@ -584,25 +650,31 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
     tick(1);
     // (this barrier also keeps the threads of a group within one tile of each other: a parity wait cannot tell phase
     // u from u + 2)
-    group_sync<NT>(g);
+    tok |= group_sync<NT>(g);
     tick(2);                        // group barrier
-    unsigned char* const smb = reinterpret_cast<unsigned char*>(S.stage[s]);
+    unsigned char* smb = reinterpret_cast<unsigned char*>(S.stage[s]);
     if (init) {
 #pragma unroll
       for (int i = 0; i < PER; ++i) *reinterpret_cast<c128*>(smb + ((t + (uint32_t)i * NT) << 4)) = make_double2(0.0, 0.0);
-      group_sync<NT>(g);
+      tok |= group_sync<NT>(g);
       if (t == 0) S.stage[s][swz(init_local)] = make_double2(1.0, 0.0);
-      group_sync<NT>(g);
+      tok |= group_sync<NT>(g);
     } else {
-      mbar_wait(&S.full[s][u & 1u], (u >> 1) & 1u);
+      tok |= mbar_wait(&S.full[s][u & 1u], (u >> 1) & 1u);
     }
+    smb += tok;                     // (0: keeps the statements above alive and in front of the loads below)
     tick(3);                        // wait for the tile
     c128 v[PER];
+    uint32_t vc = 0;                // cursor into the per-thread stream (bytes)
     for (int rd = 0; rd < n_rounds; ++rd) {
-      const uint4 hq = *reinterpret_cast<const uint4*>(&S.rh[rd]);
-      const int ng = (int)(hq.x & 0xFFFFu), first = (int)(hq.x >> 16);
-      const uint32_t srb[5] = {(hq.y & 0xFFFFu) << 4, (hq.y >> 16) << 4, (hq.z & 0xFFFFu) << 4, (hq.z >> 16) << 4, 0u};
-      const uint32_t lt = S.thr[rd][t], stb = swz(lt) << 4;
+      const uint32_t ngf = P.rh[rd].ng_first;
+      const int ng = (int)(ngf & 0xFFFFu), first = (int)(ngf >> 16);
+      // the per-thread side of the round: slot masks of the register bits, this thread's local index bits
+      vc = (vc + 15u) & ~15u;       // (4-word items start on 16 bytes)
+      const uint4 vh = *reinterpret_cast<const uint4*>(vsb + vc);
+      vc += 16u;
+      const uint32_t srb[5] = {(vh.x & 0xFFFFu) << 4, (vh.x >> 16) << 4, (vh.y & 0xFFFFu) << 4, (vh.y >> 16) << 4, 0u};
+      const uint32_t lt = *reinterpret_cast<const uint16_t*>(thrb + vh.z), stb = swz(lt) << 4;
 
       // Gray-code walk over the 2^R register amplitudes: one XOR per shared-memory address
       {
@@ -618,105 +690,114 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
       // ~4 000 cycles, so there is still a wait here; leaving the refill until later in the round -- a test inside the
       // record loop -- cost more in the loop than the wait: 208 against 183 ms on the 30-qubit layer circuit.)
       if (store_pending) {
-        bulk_wait_read();
+        tok |= bulk_wait_read<0>();
         if (!init) request(j - kGroups + kStages);
         store_pending = false;
       }
       tick(4);                      // round: registers <- shared memory (issue), refill of the previous buffer
-      // the next record is fetched while the current one runs
-      uint4 q = S.rec[first];
+      // The records and their payload are kernel parameters: `q`, the payload offsets and every coefficient that does
+      // not depend on the thread are uniform-register values (see PassConst).
       for (int gi = first; gi < first + ng; ++gi) {
-        const uint4 nq = S.rec[gi + 1];
+        const uint4 q = P.rec[gi];
         const uint32_t op = q.x & 3u;
-        const double* __restrict__ pay_t = reinterpret_cast<const double*>(pay_b + ((q.y & 0xFFFFu) << 4));
-        const double* __restrict__ pay_d = reinterpret_cast<const double*>(pay_b + ((q.y >> 16) << 4));
+        const uint32_t off_t = (q.y & 0xFFFFu) * 2u, off_d = (q.y >> 16) * 2u;      // in doubles, into P.pay / S.pay
+        const double* __restrict__ pay_t = P.pay + off_t;
+        const double* __restrict__ pay_d = P.pay + off_d;
         if (op != 0u) {
           const uint32_t rot = (q.x >> 2) & 15u;
-          if (rot) layer_apply<R>(v, pay_t, rot);
+          if (rot) layer_apply<R>(v, pay_t, rot, (q.x >> 20) & 15u);
           if (op == 1u) {
             if (q.x & 0x100u) {
-              // one table per combination of (up to) three selector bits: index bits outside the tile (CTA-uniform per
-              // tile) or thread bits of the tile (48 + local position); 63 = none, which reads as 0
-              uint32_t var = 0, stride = 1;
-              if (q.z != 0x3F3F3Fu) {
-                const uint32_t p1 = q.z & 63u, p2 = (q.z >> 8) & 63u, p3 = (q.z >> 16) & 63u;
+              if (!(q.x & 0x200u)) {
+                tab_apply<R>(v, reinterpret_cast<const double2*>(pay_d));           // one table for everybody: UR operands
+              } else {
+                // one table per combination of (up to) three selector bits: index bits outside the tile (constant per
+                // tile) or thread bits of the tile (48 + local position); 63 = none, which reads as 0
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(vsb + vc);
+                vc += 4u;
+                const uint32_t p1 = w & 63u, p2 = (w >> 6) & 63u, p3 = (w >> 12) & 63u;
                 const uint64_t sel = fixedidx | ((uint64_t)lt << 48);
-                var = (uint32_t)((sel >> p1) & 1ull) | ((uint32_t)((sel >> p2) & 1ull) << 1) |
-                      ((uint32_t)((sel >> p3) & 1ull) << 2);
-                stride = 1u << ((p1 != 63u) + (p2 != 63u) + (p3 != 63u));
+                const uint32_t var = (uint32_t)((sel >> p1) & 1ull) | ((uint32_t)((sel >> p2) & 1ull) << 1) |
+                                     ((uint32_t)((sel >> p3) & 1ull) << 2);
+                tab_apply<R>(v, reinterpret_cast<const double2*>(pay_b + ((w >> 18) << 4)) + var * kTabPitch);
               }
-              tab_apply<R>(v, reinterpret_cast<const double2*>(pay_d) + var, stride);
             }
           } else {
-            const uint32_t dk = (q.x >> 9) & 7u, fan = (q.x >> 12) & 63u;
-            c128 wt;
+            const uint32_t dk = (q.x >> 9) & 7u, jf = (q.x >> 6) & 7u;
             if (dk == D_W) {
-              wt = *reinterpret_cast<const double2*>(pay_d);             // the factor itself
+              run_phase1<R>(v, jf, pay_d);                               // the factor itself, the same for every thread
             } else {
-              wt = fixp[fan];
-              if (dk != D_FIX) {
-                const unsigned char* tb = reinterpret_cast<const unsigned char*>(pay_d);
+              const uint32_t w = *reinterpret_cast<const uint32_t*>(vsb + vc);
+              vc += 4u;
+              c128 wt = fixp[w & 63u];
+              if (!(dk & 4u)) {                                          // (not D_FIX: thread tables)
+                const unsigned char* const tb = pay_b + ((w >> 8) << 4);
                 wt = cmul(wt, cmul(*reinterpret_cast<const double2*>(tb + lane_off),
                                    *reinterpret_cast<const double2*>(tb + warp_off)));
               }
-            }
-            const double2* __restrict__ reg_t = reinterpret_cast<const double2*>(pay_d) + 32 + NWARP_T;
-            switch ((q.x >> 6) & 7u) {
-#define B200_F_CASE(J)                                              \
-              case J:                                               \
-                if (dk == D_FAN) fan_apply<R, J>(v, wt, reg_t);     \
-                else fant_apply<R, J>(v, wt);                       \
-                break;
-              B200_F_CASE(0) B200_F_CASE(1) B200_F_CASE(2) B200_F_CASE(3) B200_F_CASE(4)
-#undef B200_F_CASE
-              default: break;
+              run_fan<R>(v, jf, (dk & 2u) != 0u && !(dk & 4u), wt, reinterpret_cast<const double2*>(pay_d) + 32 + NWARP_T);
             }
           }
         } else {
-          const uint32_t lm = q.z & 0xFFFFu, rm = q.z >> 16, fmh = q.x >> 24;
-          // fixed-bit condition: CTA-uniform; thread-bit condition: per thread
-          const bool active = ((fx_lo & q.w) == q.w) && ((fx_hi & fmh) == fmh) && ((lt & lm) == lm);
+          vc = (vc + 15u) & ~15u;
+          const uint4 w = *reinterpret_cast<const uint4*>(vsb + vc);
+          vc += 16u;
+          const uint32_t qz = w.x, qw = w.y, fmh = w.z & 0xFFu, fanv = w.z >> 8;
+          // rm: the register-bit mask as a uniform value (branches) and rmv as a per-thread one (predicates: a few
+          // instructions predicated by a uniform condition cost the uniform registers just like the jump tables)
+          const uint32_t lm = qz & 0xFFFFu, rm = q.z >> 16, rmv = qz >> 16;
+          // fixed-bit condition: constant per tile; thread-bit condition: per thread
+          const bool active = ((fx_lo & qw) == qw) && ((fx_hi & fmh) == fmh) && ((lt & lm) == lm);
           if (active) {
-            const uint32_t key1 = (q.x >> 2) & 0xFFu, key2 = (q.x >> 10) & 0xFFu, fan = (q.x >> 18) & 63u;
-            if (key1 == kKeyLayer) layer_apply<R>(v, pay_t, rm & 15u);
-            else if (FULL && key1 != 0u) run_target<R>(v, key1, rm, pay_t);
+            const uint32_t key1 = (q.x >> 2) & 0xFFu, key2 = (q.x >> 10) & 0xFFu;
+            if (key1 == kKeyLayer) {
+              uint32_t m3 = 0;
+#pragma unroll
+              for (int b = 0; b < 4; ++b) m3 |= (pay_t[4 * b + 2] != 0.0 ? 1u : 0u) << b;
+              layer_apply<R>(v, pay_t, rm & 15u, m3);
+            }
+            else if (FULL && key1 != 0u) run_target<R>(v, key1, rmv, pay_t);
             if (key2 == kKeyTab) {
-              const uint32_t p1 = (rm >> 4) & 63u, p2 = (rm >> 10) & 63u, p3 = fan;
+              const uint32_t p1 = (rmv >> 4) & 63u, p2 = (rmv >> 10) & 63u, p3 = fanv;
               const uint64_t sel = fixedidx | ((uint64_t)lt << 48);
               const uint32_t var = (uint32_t)((sel >> p1) & 1ull) | ((uint32_t)((sel >> p2) & 1ull) << 1) |
                                    ((uint32_t)((sel >> p3) & 1ull) << 2);
-              const uint32_t m = (p1 != 63u) + (p2 != 63u) + (p3 != 63u);
-              tab_apply<R>(v, reinterpret_cast<const double2*>(pay_d) + var, 1u << m);
+              tab_apply<R>(v, reinterpret_cast<const double2*>(pay_b + (w.w << 4)) + var * kTabPitch);
             } else if (key2 != 0u) {
-              const uint32_t dk = key2 & 7u;
-              c128 wt = make_double2(1.0, 0.0);
-              if (dk == D_FANT || dk == D_FAN) {
-                const unsigned char* tb = reinterpret_cast<const unsigned char*>(pay_d);
-                wt = cmul(fixp[fan], cmul(*reinterpret_cast<const double2*>(tb + lane_off),
-                                          *reinterpret_cast<const double2*>(tb + warp_off)));
-              } else if (dk == D_FIX) {
-                wt = fixp[fan];
-              } else if (dk == D_W) {
-                wt = *reinterpret_cast<const double2*>(pay_d);           // the factor itself
+              // kinds: fan with thread tables 1, + register table 2, phase under a register mask 3, plain factor 4, fan
+              // without tables 5 -- told apart by bit tests (see run_target)
+              const uint32_t dk = key2 & 7u, jd = key2 >> 3;
+              if (dk & 4u) {
+                if (dk & 1u) run_fan<R>(v, jd, false, fixp[fanv], nullptr);
+                else run_phase1<R>(v, jd, pay_d);
+              } else if ((dk & 1u) && (dk & 2u)) {
+                run_phase_mask<R>(v, rmv, pay_d);
+              } else {
+                const unsigned char* const tb = pay_b + (w.w << 4);
+                const c128 wt = cmul(fixp[fanv], cmul(*reinterpret_cast<const double2*>(tb + lane_off),
+                                                      *reinterpret_cast<const double2*>(tb + warp_off)));
+                run_fan<R>(v, jd, (dk & 2u) != 0u, wt, reinterpret_cast<const double2*>(pay_d) + 32 + NWARP_T);
               }
-              run_diag<R, NWARP_T>(v, key2, rm, pay_d, wt);
             }
           }
         }
-        q = nq;
       }
       tick(5);                      // round: gates
       {
-        uint32_t so = stb;
+        // the 16 slot addresses are derived again (kept live across the gates they cost 16 registers of the 128)
+        uint32_t lt2;
+        asm("mov.u32 %0, %1;" : "=r"(lt2) : "r"(lt));
+        uint32_t so = swz(lt2) << 4;
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
           if (i) so ^= srb[ctz_c(i)];
           *reinterpret_cast<c128*>(smb + so) = v[i ^ (i >> 1)];
         }
       }
-      if (rd == n_rounds - 1) fence_async();      // the TMA store below reads what this thread just wrote
+      if (rd == n_rounds - 1) tok |= fence_async();      // the TMA store below reads what this thread just wrote
       tick(6);                      // round: shared memory <- registers
-      group_sync<NT>(g);
+      tok |= group_sync<NT>(g);
+      smb += tok;
       tick(7);                      // round: barrier
     }
     // the finished tile leaves through the TMA unit (every warp of the group issues its share of the sub-copies)
@@ -725,6 +806,7 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
     tick(8);                        // issue the stores
   }
   bulk_wait_all();
+  if (tok != 0u && phase_cycles != nullptr) phase_cycles[15] = tok;      // never true: tok is 0 (keeps the last statements alive)
 }
 
 // ---- host side: the tile as a tensor box -------------------------------------------------------------------------
@@ -813,7 +895,7 @@ static int build_tile_map(b200_state* st, const int* tile, int a, TileMapDev& tm
 static_assert(sizeof(TileSmem<12>) <= 232448, "the 2^12 tile's shared memory exceeds the 227 KB a CTA can have");
 
 template <int A, bool FULL>
-static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals, const int* tile, bool init,
+static int launch(b200_state* st, const PassConst& pc, const uint64_t* d_desc, const double* d_reals, const int* tile, bool init,
                   uint64_t init_tile, uint32_t init_local) {
   constexpr int NT = 1 << (A - R);
   const size_t smem = sizeof(TileSmem<A>);
@@ -831,7 +913,7 @@ static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals,
   const unsigned grid = (unsigned)(n_tiles < (uint64_t)kSMs ? n_tiles : (uint64_t)kSMs);
   static const bool timing = getenv("B200_TILE_TIMING") != nullptr;
   if (!timing) {
-    k_tile<A, FULL, false><<<grid, kGroups * NT, smem, st->stream>>>(map, tm, n_tiles, st->index_offset, d_desc, d_reals,
+    k_tile<A, FULL, false><<<grid, kGroups * NT, smem, st->stream>>>(map, tm, pc, n_tiles, st->index_offset, d_desc, d_reals,
                                                                      init ? 2u : 0u, init_tile, init_local, nullptr);
     st->launches++;
     B200_CUDA(cudaGetLastError());
@@ -841,7 +923,7 @@ static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals,
   unsigned long long* d_cyc = nullptr;
   B200_CUDA(cudaMalloc(&d_cyc, kPhases * sizeof(unsigned long long)));
   B200_CUDA(cudaMemsetAsync(d_cyc, 0, kPhases * sizeof(unsigned long long), st->stream));
-  k_tile<A, FULL, true><<<grid, kGroups * NT, smem, st->stream>>>(map, tm, n_tiles, st->index_offset, d_desc, d_reals,
+  k_tile<A, FULL, true><<<grid, kGroups * NT, smem, st->stream>>>(map, tm, pc, n_tiles, st->index_offset, d_desc, d_reals,
                                                                   init ? 2u : 0u, init_tile, init_local, d_cyc);
   st->launches++;
   B200_CUDA(cudaGetLastError());
@@ -861,7 +943,7 @@ static int launch(b200_state* st, const uint64_t* d_desc, const double* d_reals,
 }
 
 int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_desc, int wlen,
-                     const double* d_reals, size_t n_reals, uint64_t init_index) {
+                     const double* d_reals, const double* h_reals, size_t n_reals, uint64_t init_index) {
   B200_REQUIRE(wlen >= 5, "TILE descriptor too short");
   const uint64_t h0 = h_desc[0];
   const int A = (int)(h0 & 0xFF), c = (int)((h0 >> 8) & 0xFF), Rd = (int)((h0 >> 16) & 0xFF);
@@ -890,20 +972,95 @@ int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_d
                "TILE descriptor: fan records too long");
   B200_REQUIRE((h_desc[4] >> 32) <= (uint64_t)kMaxPayload && (h_desc[4] & 0xFFFFFFFFu) + (h_desc[4] >> 32) <= n_reals,
                "TILE descriptor: payload range too long or outside the reals pool");
+  // The pass as the kernel wants it (PassConst): round headers, one 16-byte record per gate record of the descriptor,
+  // and the payload.  (The kernel decoded the descriptor itself, once per CTA, until the records moved into the constant
+  // bank.)
+  static thread_local PassConst pc;
+  const uint32_t pay_lo = (uint32_t)(h_desc[4] & 0xFFFFFFFFu), pay_len = (uint32_t)(h_desc[4] >> 32);
+  pc.n_rounds = (uint32_t)n_rounds;
+  pc.n_fans = (uint32_t)n_fans;
+  pc.dir_off = (uint32_t)dir_off;
+  pc.rounds_off = (uint32_t)rounds_off;
+  pc.pay_lo = pay_lo;
+  pc.pay_len = pay_len;
+  pc.pad1 = 0;
+  for (uint32_t i = 0; i < pay_len; ++i) pc.pay[i] = h_reals[pay_lo + i];
+  auto in_payload = [&](uint64_t off, uint32_t len) { return off >= pay_lo && off + len <= (uint64_t)pay_lo + pay_len; };
   uint64_t pos = rounds_off, gates = 0;
+  uint32_t nvs = 0;               // words of the per-thread stream
   bool full = false;              // does any record need a general target stage (kinds 1..3)?
   for (int rd = 0; rd < n_rounds; ++rd) {
     B200_REQUIRE(pos + 3 <= (uint64_t)wlen, "TILE descriptor: round header out of range");
     const uint64_t ng = h_desc[pos] & 0xFFFF, nw = h_desc[pos] >> 16;
     B200_REQUIRE(nw >= 3 + 3 * ng && pos + nw <= (uint64_t)wlen, "TILE descriptor: round length out of range");
-    for (uint64_t g = 0; g < ng; ++g) {
-      const int tk = (int)(h_desc[pos + 3 + 3 * g] & 0xFF);
+    B200_REQUIRE(gates + ng <= (uint64_t)kMaxGates, "TILE descriptor: too many gates");
+    RoundConst& rc = pc.rh[rd];
+    B200_REQUIRE(nvs + 8 <= (uint32_t)kMaxVsWords, "TILE descriptor: too many records");
+    rc.ng_first = (uint32_t)ng | ((uint32_t)gates << 16);
+    rc.pad = 0;
+    rc.o_lo = h_desc[pos + 1];
+    rc.o_hi = h_desc[pos + 2];
+    uint32_t srb[4];
+    for (int k = 0; k < R; ++k) srb[k] = swz(1u << ((rc.o_lo >> (8 * k)) & 0xFF)) & 0xFFFFu;
+    rc.srb01 = srb[0] | (srb[1] << 16);
+    rc.srb23 = srb[2] | (srb[3] << 16);
+    while (nvs & 3u) pc.vs[nvs++] = 0;                       // 4-word items start on 16 bytes
+    pc.vs[nvs++] = rc.srb01;
+    pc.vs[nvs++] = rc.srb23;
+    pc.vs[nvs++] = (uint32_t)rd * (2u << (A - R));          // the round's row of TileSmem::thr, in bytes
+    pc.vs[nvs++] = 0;
+    for (uint64_t gi = 0; gi < ng; ++gi) {
+      const uint64_t g0 = h_desc[pos + 3 + 3 * gi], fm = h_desc[pos + 4 + 3 * gi], roffs = h_desc[pos + 5 + 3 * gi];
+      const uint32_t tk = (uint32_t)(g0 & 0xFF), j = (uint32_t)((g0 >> 8) & 0xFF), dk = (uint32_t)((g0 >> 16) & 0xFF);
+      const uint32_t fan = (uint32_t)((g0 >> 24) & 0xFF);
+      const uint32_t lm = (uint32_t)((g0 >> 32) & 0xFFFF), rm = (uint32_t)((g0 >> 48) & 0xFFFF);
       full |= tk == T_MATC || tk == T_MATR || tk == T_X;
+      const bool has_t = !(tk == T_NONE || tk == T_X), has_d = dk != D_NONE;
+      B200_REQUIRE(!has_t || in_payload(roffs & 0xFFFFFFFFu, tk == T_LAYER ? 16 : 8), "TILE descriptor: target payload outside the pass's range");
+      B200_REQUIRE(!has_d || in_payload(roffs >> 32, 2), "TILE descriptor: diag payload outside the pass's range");
+      const uint32_t pt = has_t ? (((uint32_t)roffs - pay_lo) >> 1) : 0u;
+      const uint32_t pd = has_d ? (((uint32_t)(roffs >> 32) - pay_lo) >> 1) : 0u;
+      const uint32_t jj = j < (uint32_t)R ? j : 4u;            // 4 = no register target ("every amplitude")
+      const bool plain = lm == 0 && fm == 0 && (tk == T_NONE || tk == T_LAYER);
+      uint32_t rot = 0, rot3 = 0;                                // rotations of a layer; those with a third update
+      if (tk == T_LAYER) {
+        rot = rm & 15u;
+        for (uint32_t b = 0; b < 4u; ++b)
+          if (((rot >> b) & 1u) && h_reals[(uint32_t)roffs + 4u * b + 2u] != 0.0) rot3 |= 1u << b;
+      }
+      uint4 rec;
+      rec.y = pt | (pd << 16);
+      B200_REQUIRE(nvs + 8 <= (uint32_t)kMaxVsWords, "TILE descriptor: too many records");
+      if (plain && (dk == D_NONE || dk == D_TAB)) {
+        const uint32_t p1 = (rm >> 4) & 63u, p2 = (rm >> 10) & 63u, p3 = fan & 63u;
+        const bool variants = dk == D_TAB && !(p1 == 63u && p2 == 63u && p3 == 63u);
+        rec.x = 1u | (rot << 2) | (dk == D_TAB ? 0x100u : 0u) | (variants ? 0x200u : 0u) | (rot3 << 20);
+        rec.z = rec.w = 0;
+        if (variants) pc.vs[nvs++] = p1 | (p2 << 6) | (p3 << 12) | (pd << 18);
+      } else if (plain && (dk == D_FANT || dk == D_FAN || dk == D_W || dk == D_FIX)) {
+        rec.x = 2u | (rot << 2) | (jj << 6) | (dk << 9) | ((fan & 63u) << 12) | (rot3 << 20);
+        rec.z = rec.w = 0;
+        if (dk != D_W) pc.vs[nvs++] = (fan & 63u) | (pd << 8);
+      } else {
+        while (nvs & 3u) pc.vs[nvs++] = 0;
+        pc.vs[nvs++] = lm | (rm << 16);
+        pc.vs[nvs++] = (uint32_t)fm;
+        pc.vs[nvs++] = (uint32_t)(fm >> 32) | ((fan & 63u) << 8);
+        pc.vs[nvs++] = pd;
+        const uint32_t key1 = tk == T_NONE ? 0u : tk == T_LAYER ? kKeyLayer : 16u * jj + tk + (rm != 0 ? 8u : 0u);
+        const uint32_t key2 = dk == D_NONE ? 0u : dk == D_TAB ? kKeyTab : 8u * jj + dk;
+        rec.x = (key1 << 2) | (key2 << 10) | ((fan & 63u) << 18) | ((uint32_t)(fm >> 32) << 24);
+        rec.z = lm | (rm << 16);
+        rec.w = (uint32_t)fm;
+      }
+      pc.rec[gates + gi] = rec;
     }
     gates += ng;
     pos += nw;
   }
   B200_REQUIRE(pos == (uint64_t)wlen && gates <= (uint64_t)kMaxGates, "TILE descriptor: bad round lengths or too many gates");
+  pc.rec[gates] = make_uint4(0, 0, 0, 0);
+  pc.n_vs = nvs;
   const bool init = init_index != kNoInit;
   uint64_t init_tile = ~0ull;
   uint32_t init_local = 0;
@@ -918,12 +1075,12 @@ int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_d
       if (!in_tile[b]) init_tile |= ((init_index >> b) & 1ull) << k++;
   }
   switch (A) {
-    case 9:  return launch<9, true>(st, d_desc, d_reals, tile, init, init_tile, init_local);
-    case 10: return launch<10, true>(st, d_desc, d_reals, tile, init, init_tile, init_local);
-    case 11: return launch<11, true>(st, d_desc, d_reals, tile, init, init_tile, init_local);
+    case 9:  return launch<9, true>(st, pc, d_desc, d_reals, tile, init, init_tile, init_local);
+    case 10: return launch<10, true>(st, pc, d_desc, d_reals, tile, init, init_tile, init_local);
+    case 11: return launch<11, true>(st, pc, d_desc, d_reals, tile, init, init_tile, init_local);
     // the production tile size also exists without the general target stages (see k_tile)
-    case 12: return full ? launch<12, true>(st, d_desc, d_reals, tile, init, init_tile, init_local)
-                         : launch<12, false>(st, d_desc, d_reals, tile, init, init_tile, init_local);
+    case 12: return full ? launch<12, true>(st, pc, d_desc, d_reals, tile, init, init_tile, init_local)
+                         : launch<12, false>(st, pc, d_desc, d_reals, tile, init, init_tile, init_local);
     default:
       snprintf(msg, sizeof msg, "TILE descriptor: tile size 2^%d is not built (9..12)", A);
       set_error(msg);

@@ -40,6 +40,7 @@ D_NONE, D_FANT, D_FAN, D_PHASE = 0, 1, 2, 3         # diagonal stage (fan withou
 D_W, D_FIX = 4, 5                                   # ... fan without entries / with entries outside the tile only
 D_TAB = 6                                           # ... one factor per register amplitude
 MAX_GATES = 160          # per pass (record slots in csrc/tile.cu)
+TAB_PITCH = 17            # complex entries between the variants of a record's table (csrc/tile.cu kTabPitch)
 MAX_PAYLOAD = 2560       # float64 payload of one pass (shared-memory copy in csrc/tile.cu)
 MAX_FAN_WORDS = 512      # fan directory + records of one pass (shared-memory copy in csrc/tile.cu)
 MAX_FANS = 64            # per pass (shared-memory slots in csrc/tile.cu)
@@ -927,7 +928,8 @@ class _Group:
         if self.has_tab:
             assert self.diag is None
             m = len(self.sel_bits)
-            tabs = np.ones((1 << self.r, 1 << m), dtype=complex)          # [rho][variant]
+            # [variant][rho], variants TAB_PITCH entries apart (csrc/tile.cu: compile-time offsets, no bank conflicts)
+            tabs = np.ones((1 << m, TAB_PITCH if m else 1 << self.r), dtype=complex)
             for var in range(1 << m):
                 on = {q for i, q in enumerate(self.sel_bits) if (var >> i) & 1}
                 t = self.tab.copy()
@@ -941,7 +943,7 @@ class _Group:
                     for rho in range(1 << self.r):
                         if kt is None or (rho >> kt) & 1:
                             t[rho] *= f
-                tabs[:, var] = t
+                tabs[var, :1 << self.r] = t
             tabs = list(tabs.reshape(-1))
             kw.update(dk=D_TAB, roff_d=prog.add_reals(tabs), fid=p[2])
             kw.setdefault("rm", sel)
