@@ -412,7 +412,7 @@ constexpr int kMaxRounds = 6;     // planner.PlanConfig.max_rounds
 constexpr int kSpreadTabs = 5;     // 6 bits of the tile number each: up to 30 non-tile index bits
 constexpr int kStages = 3;         // tile buffers in the ring
 constexpr int kGroups = 2;         // compute groups taking alternate tiles
-constexpr int R = 4;               // register bits per round (2^R amplitudes per thread)
+constexpr int kMaxR = 4;           // register bits per round the library is built for (2^R amplitudes per thread)
 
 constexpr int kMaxPayload = 2560;  // float64 payload of one pass kept in shared memory (planner.MAX_PAYLOAD)
 constexpr int kMaxFanWords = 512;  // fan directory + records of the pass's fans (planner keeps a pass below this)
@@ -471,7 +471,7 @@ struct TileMapDev {
   uint32_t sub_amps;               // amplitudes per copy
 };
 
-template <int A>
+template <int A, int RB>
 struct TileSmem {
   c128 stage[kStages][1 << A];     // 1024-byte aligned (SWIZZLE_128B atoms): first member of the dynamic allocation
   c128 fix[kGroups][kMaxFans];     // per-tile fan products, one set per compute group
@@ -479,7 +479,8 @@ struct TileSmem {
   double pay[kMaxPayload];         // copy of PassConst::pay for the reads indexed per thread (fan tables, table variants)
   uint64_t fanw[kMaxFanWords];     // fan directory and records (entry counts, payload offsets, fixed-bit masks)
   alignas(16) uint32_t vs[kMaxVsWords];   // copy of PassConst::vs
-  uint16_t thr[kMaxRounds][1 << (A - R)];   // per round, per thread: its local index bits
+  // per round: the local index bits a thread contributes, as (lane part)[32] | (warp part)[up to 32]
+  uint16_t thr[kMaxRounds][64];
   uint64_t full[kStages][2];       // the tile's TMA load has landed; index = use of the stage & 1
 };
 
@@ -487,15 +488,16 @@ struct TileSmem {
 // FULL = false leaves out the general target stages (complex / real 2x2, pair swap, their controlled forms): a pass
 // of 1-qubit unitaries and phases needs none of them, and the kernel without their 24 unrolled bodies runs every
 // record faster (round 1: 45.2 -> 41.0 ms on the 30-qubit QFT).
-template <int A, bool FULL, bool TIMING>
-__global__ void __launch_bounds__(kGroups * (1 << (A - R)), 1)
+template <int A, int RB, bool FULL, bool TIMING>
+__global__ void __launch_bounds__(kGroups * (1 << (A - RB)), 1)
 k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMapDev tm, const __grid_constant__ PassConst P,
        uint64_t n_tiles, uint64_t index_offset, const uint64_t* __restrict__ desc, const double* __restrict__ reals,
        uint32_t flags, uint64_t init_tile, uint32_t init_local, unsigned long long* __restrict__ phase_cycles) {
+  constexpr int R = RB;            // register bits per round (2^R amplitudes per thread)
   constexpr int NT = 1 << (A - R), PER = 1 << R, NTB = A - R;
   constexpr int NWARP_T = (NTB > 5) ? (1 << (NTB - 5)) : 1;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  TileSmem<A>& S = *reinterpret_cast<TileSmem<A>*>(smem_raw);
+  TileSmem<A, RB>& S = *reinterpret_cast<TileSmem<A, RB>*>(smem_raw);
 
   uint32_t tid;                    // (volatile: ptxas otherwise re-reads SR_TID.X inside the record loop)
   asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
@@ -525,9 +527,10 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
   }
   for (int rd = 0; rd < n_rounds; ++rd) {
     const uint64_t o_lo = P.rh[rd].o_lo, o_hi = P.rh[rd].o_hi;
-    for (uint32_t t = tid; t < (uint32_t)NT; t += blockDim.x) {
+    for (uint32_t t = tid; t < 64u; t += blockDim.x) {        // t < 32: thread bits 0..4 (lane), else bits 5.. (warp)
+      const uint32_t bits = t < 32u ? t : (t - 32u) << 5;
       uint32_t lt = 0;
-      for (int b = 0; b < NTB; ++b) lt |= ((t >> b) & 1u) << byte_of(o_lo, o_hi, R + b);
+      for (int b = 0; b < NTB; ++b) lt |= ((bits >> b) & 1u) << byte_of(o_lo, o_hi, R + b);
       S.thr[rd][t] = (uint16_t)lt;
     }
   }
@@ -557,7 +560,8 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
   const uint32_t lane_off = lane << 4, warp_off = (32u + (NWARP_T > 1 ? warp : 0u)) << 4;      // into a fan's tables
   c128* const fixp = S.fix[gv];
   const unsigned char* const vsb = reinterpret_cast<const unsigned char*>(S.vs);
-  const unsigned char* const thrb = reinterpret_cast<const unsigned char*>(&S.thr[0][t]);
+  const unsigned char* const thrb_l = reinterpret_cast<const unsigned char*>(&S.thr[0][lane]);
+  const unsigned char* const thrb_w = reinterpret_cast<const unsigned char*>(&S.thr[0][32u + warp]);
   unsigned char* const pay_b = reinterpret_cast<unsigned char*>(S.pay);
   // The sub-copies of a tile are issued by DIFFERENT warps of its group: a TMA instruction is a uniform-datapath
   // op, so the lanes of one warp that issue one each are served one after the other (~110 cycles per copy: with all
@@ -674,7 +678,9 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
       const uint4 vh = *reinterpret_cast<const uint4*>(vsb + vc);
       vc += 16u;
       const uint32_t srb[5] = {(vh.x & 0xFFFFu) << 4, (vh.x >> 16) << 4, (vh.y & 0xFFFFu) << 4, (vh.y >> 16) << 4, 0u};
-      const uint32_t lt = *reinterpret_cast<const uint16_t*>(thrb + vh.z), stb = swz(lt) << 4;
+      const uint32_t lt = (uint32_t)*reinterpret_cast<const uint16_t*>(thrb_l + vh.z) |
+                          (uint32_t)*reinterpret_cast<const uint16_t*>(thrb_w + vh.z);
+      const uint32_t stb = swz(lt) << 4;
 
       // Gray-code walk over the 2^R register amplitudes: one XOR per shared-memory address
       {
@@ -697,8 +703,9 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
       tick(4);                      // round: registers <- shared memory (issue), refill of the previous buffer
       // The records and their payload are kernel parameters: `q`, the payload offsets and every coefficient that does
       // not depend on the thread are uniform-register values (see PassConst).
+      uint4 q = P.rec[first];
       for (int gi = first; gi < first + ng; ++gi) {
-        const uint4 q = P.rec[gi];
+        const uint4 nq = P.rec[gi + 1];             // (the next record is on its way while this one runs)
         const uint32_t op = q.x & 3u;
         const uint32_t off_t = (q.y & 0xFFFFu) * 2u, off_d = (q.y >> 16) * 2u;      // in doubles, into P.pay / S.pay
         const double* __restrict__ pay_t = P.pay + off_t;
@@ -781,6 +788,7 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
             }
           }
         }
+        q = nq;
       }
       tick(5);                      // round: gates
       {
@@ -892,17 +900,18 @@ static int build_tile_map(b200_state* st, const int* tile, int a, TileMapDev& tm
   return 0;
 }
 
-static_assert(sizeof(TileSmem<12>) <= 232448, "the 2^12 tile's shared memory exceeds the 227 KB a CTA can have");
+static_assert(sizeof(TileSmem<12, 4>) <= 232448,
+              "the 2^12 tile's shared memory exceeds the 227 KB a CTA can have");
 
-template <int A, bool FULL>
+template <int A, int RB, bool FULL>
 static int launch(b200_state* st, const PassConst& pc, const uint64_t* d_desc, const double* d_reals, const int* tile, bool init,
                   uint64_t init_tile, uint32_t init_local) {
-  constexpr int NT = 1 << (A - R);
-  const size_t smem = sizeof(TileSmem<A>);
+  constexpr int NT = 1 << (A - RB);
+  const size_t smem = sizeof(TileSmem<A, RB>);
   static bool configured[64] = {};
   if (!configured[st->device & 63]) {
-    B200_CUDA(cudaFuncSetAttribute(k_tile<A, FULL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B200_CUDA(cudaFuncSetAttribute(k_tile<A, FULL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(k_tile<A, RB, FULL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(k_tile<A, RB, FULL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[st->device & 63] = true;
   }
   TileMapDev tm;
@@ -913,7 +922,7 @@ static int launch(b200_state* st, const PassConst& pc, const uint64_t* d_desc, c
   const unsigned grid = (unsigned)(n_tiles < (uint64_t)kSMs ? n_tiles : (uint64_t)kSMs);
   static const bool timing = getenv("B200_TILE_TIMING") != nullptr;
   if (!timing) {
-    k_tile<A, FULL, false><<<grid, kGroups * NT, smem, st->stream>>>(map, tm, pc, n_tiles, st->index_offset, d_desc, d_reals,
+    k_tile<A, RB, FULL, false><<<grid, kGroups * NT, smem, st->stream>>>(map, tm, pc, n_tiles, st->index_offset, d_desc, d_reals,
                                                                      init ? 2u : 0u, init_tile, init_local, nullptr);
     st->launches++;
     B200_CUDA(cudaGetLastError());
@@ -923,7 +932,7 @@ static int launch(b200_state* st, const PassConst& pc, const uint64_t* d_desc, c
   unsigned long long* d_cyc = nullptr;
   B200_CUDA(cudaMalloc(&d_cyc, kPhases * sizeof(unsigned long long)));
   B200_CUDA(cudaMemsetAsync(d_cyc, 0, kPhases * sizeof(unsigned long long), st->stream));
-  k_tile<A, FULL, true><<<grid, kGroups * NT, smem, st->stream>>>(map, tm, pc, n_tiles, st->index_offset, d_desc, d_reals,
+  k_tile<A, RB, FULL, true><<<grid, kGroups * NT, smem, st->stream>>>(map, tm, pc, n_tiles, st->index_offset, d_desc, d_reals,
                                                                   init ? 2u : 0u, init_tile, init_local, d_cyc);
   st->launches++;
   B200_CUDA(cudaGetLastError());
@@ -949,7 +958,7 @@ int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_d
   const int A = (int)(h0 & 0xFF), c = (int)((h0 >> 8) & 0xFF), Rd = (int)((h0 >> 16) & 0xFF);
   const int n_rounds = (int)((h0 >> 24) & 0xFF), n_fans = (int)((h0 >> 32) & 0xFF);
   char msg[200];
-  if (A > st->n || c > A || c < 3 || Rd != R || n_fans > kMaxFans || n_rounds > kMaxRounds || st->n - A > 6 * kSpreadTabs) {
+  if (A > st->n || c > A || c < 3 || Rd != kMaxR || n_fans > kMaxFans || n_rounds > kMaxRounds || st->n - A > 6 * kSpreadTabs) {
     snprintf(msg, sizeof msg, "TILE descriptor not executable: A=%d c=%d R=%d fans=%d rounds=%d on %d qubits", A, c, Rd,
              n_fans, n_rounds, st->n);
     set_error(msg);
@@ -1000,14 +1009,14 @@ int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_d
     rc.pad = 0;
     rc.o_lo = h_desc[pos + 1];
     rc.o_hi = h_desc[pos + 2];
-    uint32_t srb[4];
-    for (int k = 0; k < R; ++k) srb[k] = swz(1u << ((rc.o_lo >> (8 * k)) & 0xFF)) & 0xFFFFu;
+    uint32_t srb[4] = {0, 0, 0, 0};
+    for (int k = 0; k < Rd; ++k) srb[k] = swz(1u << ((rc.o_lo >> (8 * k)) & 0xFF)) & 0xFFFFu;
     rc.srb01 = srb[0] | (srb[1] << 16);
     rc.srb23 = srb[2] | (srb[3] << 16);
     while (nvs & 3u) pc.vs[nvs++] = 0;                       // 4-word items start on 16 bytes
     pc.vs[nvs++] = rc.srb01;
     pc.vs[nvs++] = rc.srb23;
-    pc.vs[nvs++] = (uint32_t)rd * (2u << (A - R));          // the round's row of TileSmem::thr, in bytes
+    pc.vs[nvs++] = (uint32_t)rd * 128u;                    // the round's row of TileSmem::thr, in bytes
     pc.vs[nvs++] = 0;
     for (uint64_t gi = 0; gi < ng; ++gi) {
       const uint64_t g0 = h_desc[pos + 3 + 3 * gi], fm = h_desc[pos + 4 + 3 * gi], roffs = h_desc[pos + 5 + 3 * gi];
@@ -1020,7 +1029,7 @@ int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_d
       B200_REQUIRE(!has_d || in_payload(roffs >> 32, 2), "TILE descriptor: diag payload outside the pass's range");
       const uint32_t pt = has_t ? (((uint32_t)roffs - pay_lo) >> 1) : 0u;
       const uint32_t pd = has_d ? (((uint32_t)(roffs >> 32) - pay_lo) >> 1) : 0u;
-      const uint32_t jj = j < (uint32_t)R ? j : 4u;            // 4 = no register target ("every amplitude")
+      const uint32_t jj = j < (uint32_t)Rd ? j : 4u;            // 4 = no register target ("every amplitude")
       const bool plain = lm == 0 && fm == 0 && (tk == T_NONE || tk == T_LAYER);
       uint32_t rot = 0, rot3 = 0;                                // rotations of a layer; those with a third update
       if (tk == T_LAYER) {
@@ -1074,13 +1083,16 @@ int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_d
     for (int b = 0, k = 0; b < st->n; ++b)
       if (!in_tile[b]) init_tile |= ((init_index >> b) & 1ull) << k++;
   }
+  // (k_tile<12, 3, ...>, 8 amplitudes per thread and 2 x 512 threads at 64 registers, was built and measured in round 2:
+  // twice the warps but a third more rounds per pass -- 210 against 163 ms on the 30-qubit layer circuit, 26.7 against
+  // 22.2 ms on the QFT.  The rounds' shared-memory traffic is what a pass pays for, not latency that more warps hide.)
   switch (A) {
-    case 9:  return launch<9, true>(st, pc, d_desc, d_reals, tile, init, init_tile, init_local);
-    case 10: return launch<10, true>(st, pc, d_desc, d_reals, tile, init, init_tile, init_local);
-    case 11: return launch<11, true>(st, pc, d_desc, d_reals, tile, init, init_tile, init_local);
+    case 9:  return launch<9, 4, true>(st, pc, d_desc, d_reals, tile, init, init_tile, init_local);
+    case 10: return launch<10, 4, true>(st, pc, d_desc, d_reals, tile, init, init_tile, init_local);
+    case 11: return launch<11, 4, true>(st, pc, d_desc, d_reals, tile, init, init_tile, init_local);
     // the production tile size also exists without the general target stages (see k_tile)
-    case 12: return full ? launch<12, true>(st, pc, d_desc, d_reals, tile, init, init_tile, init_local)
-                         : launch<12, false>(st, pc, d_desc, d_reals, tile, init, init_tile, init_local);
+    case 12: return full ? launch<12, 4, true>(st, pc, d_desc, d_reals, tile, init, init_tile, init_local)
+                         : launch<12, 4, false>(st, pc, d_desc, d_reals, tile, init, init_tile, init_local);
     default:
       snprintf(msg, sizeof msg, "TILE descriptor: tile size 2^%d is not built (9..12)", A);
       set_error(msg);
