@@ -62,7 +62,7 @@ typedef struct b200_op {
 
 const char* b200_last_error(void);
 int b200_device_count(int* out);
-int b200_version(void);                 /* 102; bumped whenever the TILE descriptor format changes */
+int b200_version(void);                 /* 103; bumped whenever the TILE descriptor format changes */
 
 /* ---- state lifetime (replaces _NumPyBackendContext.__init__/prepare, numpy_backend.py:36-62) ---- */
 
@@ -85,6 +85,15 @@ int b200_state_set_index_offset(b200_state* st, uint64_t offset);
 
 int b200_apply_program(b200_state* st, const b200_op* ops, int n_ops,
                        const uint64_t* words, size_t n_words, const double* reals, size_t n_reals);
+/* The same, piece by piece: the objective loop of vqe.py:67-83 re-plans the circuit for every angle vector, and the
+   device can run the first passes while the host is still planning the later ones.  A pass takes everything it
+   needs from the host arrays at launch (kernel parameters), so a piece may be handed over as soon as it is encoded.
+   flags: B200_APPLY_ASYNC = return without waiting for the device (b200_sync / any reduction waits),
+          B200_APPLY_CONTINUE = a further piece of a program whose first piece started b200_last_program_ms's timer. */
+#define B200_APPLY_ASYNC 1
+#define B200_APPLY_CONTINUE 2
+int b200_apply_program_ex(b200_state* st, const b200_op* ops, int n_ops,
+                          const uint64_t* words, size_t n_words, const double* reals, size_t n_reals, int flags);
 /* Device time of the last b200_apply_program (CUDA events on the state's stream), in milliseconds. */
 int b200_last_program_ms(b200_state* st, double* ms);
 /* Per-op device times of the last program (only recorded while profiling is on). Returns count in *n. */

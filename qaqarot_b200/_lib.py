@@ -14,7 +14,7 @@ from typing import List, Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libb200sv.so")
-ABI_VERSION = 102            # b200_version() of the library this planner's TILE descriptors are written for
+ABI_VERSION = 103            # b200_version() of the library this planner's TILE descriptors are written for
 SOURCES = ["b200sv.cu", "sample.cu", "tile.cu", "permute.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -36,6 +36,7 @@ class Op(C.Structure):
 
 OP_MAT, OP_DIAG, OP_X, OP_SWAP, OP_PERMUTE, OP_TILE, OP_SCALE = 1, 2, 3, 4, 5, 16, 17
 OP_INIT = 18         # state := |cmask>; free when the next op is a TILE pass
+APPLY_ASYNC, APPLY_CONTINUE = 1, 2     # flags of b200_apply_program_ex
 OP_EXCHANGE = 32      # host-level: exchange index bit `target` (top local) with global bit `aux`; never sent to the C ABI
 
 _lib: Optional[C.CDLL] = None
@@ -55,6 +56,7 @@ _SIGNATURES = {
     "b200_state_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]),
     "b200_state_copy": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200_apply_program": (C.c_int, [C.c_void_p, _P(Op), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "b200_apply_program_ex": (C.c_int, [C.c_void_p, _P(Op), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]),
     "b200_last_program_ms": (C.c_int, [C.c_void_p, _P(C.c_double)]),
     "b200_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "b200_last_op_times": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _P(C.c_int)]),

@@ -63,7 +63,8 @@ class _Compiled:
     """Lowered + planned form of gates[start:], cached on the backend between runs of the same circuit."""
 
     def __init__(self, gates: Sequence, n_qubits: int, start: int, planner: Callable[..., Program],
-                 initial_layout: Optional[Sequence[int]] = None, from_zero: bool = False):
+                 initial_layout: Optional[Sequence[int]] = None, from_zero: bool = False,
+                 on_pass: Optional[Callable[[Program], None]] = None):
         self.gates = tuple(gates)
         self.n_qubits = n_qubits
         self.start = start
@@ -79,8 +80,10 @@ class _Compiled:
 
         def planner(seg, n):            # a sharded planner leaves wires where they are: thread the layout along
             free = from_zero and first[0] and getattr(user_planner, "accepts_free_layout", False)
-            first[0] = False
             kw = {"free_initial_layout": True} if free else {}
+            if first[0] and on_pass is not None and getattr(user_planner, "accepts_on_pass", False):
+                kw["on_pass"] = on_pass          # the prefix is launched pass by pass while it is being planned
+            first[0] = False
             if getattr(user_planner, "threads_layout", False):
                 prog = user_planner(seg, n, layout[0], **kw)
                 layout[0] = list(prog.final_pos)
@@ -114,6 +117,30 @@ class _Compiled:
                 and from_zero == self.from_zero
                 and (list(initial_layout) if initial_layout is not None else None) == self.initial_layout
                 and all(a is b or _same_op(a, b) for a, b in zip(gates, self.gates)))
+
+
+class _Streamer:
+    """Launches the ops of a program as the planner appends them (planner.plan's on_pass), without waiting for the
+    device: with a new angle vector every iteration (vqe.py:67-83) the plan cannot be reused, but the device can run pass
+    k while the host encodes pass k + 1."""
+
+    def __init__(self, st, init_basis: Optional[int]):
+        self.st, self.init_basis = st, init_basis
+        self.ops = self.words = self.reals = 0
+        self.first = True
+
+    def __call__(self, prog: Program) -> None:
+        n = len(prog._ops)
+        if n == self.ops:
+            return
+        self.st.apply_piece(prog, self.ops, n, self.words, self.reals, init_basis=self.init_basis if self.first else None,
+                            first=self.first)
+        self.ops, self.words, self.reals, self.first = n, len(prog._words), len(prog._reals), False
+
+    def finish(self, prog: Program) -> None:
+        self(prog)
+        if self.first and self.init_basis is not None:       # an empty program: only the preparation is left
+            self.st.set_basis(self.init_basis & (self.st.dim - 1))
 
 
 def _same_op(a, b) -> bool:
@@ -157,12 +184,14 @@ class B200Backend(_Base):
                 from .planner import DEFAULT, plan as _plan
                 _cfg = plan_config or DEFAULT
 
-                def planner(prims, n, free_initial_layout=False):
-                    return _plan(prims, n, _cfg, free_initial_layout=free_initial_layout)
+                def planner(prims, n, free_initial_layout=False, on_pass=None):
+                    return _plan(prims, n, _cfg, free_initial_layout=free_initial_layout, on_pass=on_pass)
                 planner.accepts_free_layout = True
+                planner.accepts_on_pass = True
             else:
                 planner = lambda prims, n: unfused_program(prims, n)
         self._planner = planner
+        self.stream_plans = True             # launch a newly planned circuit pass by pass (b200_apply_program_ex)
         self._work = None                    # reusable work state
         self._compiled: Optional[_Compiled] = None
         self.last_stats: Dict[str, Any] = {}
@@ -202,10 +231,13 @@ class B200Backend(_Base):
             self._work = self._state_factory(n_qubits, self.device)
         return self._work
 
-    def _compile(self, gates: Sequence, n_qubits: int, start: int, initial_layout=None, from_zero=False) -> _Compiled:
+    def _compile(self, gates: Sequence, n_qubits: int, start: int, initial_layout=None, from_zero=False,
+                 on_pass=None) -> _Compiled:
+        """`on_pass`: only used when the circuit has to be planned (no cached plan); the caller checks
+        `on_pass.ops` to see whether the prefix has already been launched."""
         c = self._compiled
         if c is None or not c.matches(gates, n_qubits, start, initial_layout, from_zero):
-            c = self._compiled = _Compiled(gates, n_qubits, start, self._planner, initial_layout, from_zero)
+            c = self._compiled = _Compiled(gates, n_qubits, start, self._planner, initial_layout, from_zero, on_pass)
         return c
 
     def _download(self, st) -> np.ndarray:
@@ -221,18 +253,23 @@ class B200Backend(_Base):
         ctx = RunContext(n_qubits)
         cache, cache_idx = (self.cache, self.cache_idx) if use_backend_cache else (None, -1)
         start = cache_idx + 1 if cache is not None else 0
-        comp = self._compile(gates, n_qubits, start, getattr(cache, "layout", None) if cache is not None else None,
-                             from_zero=cache is None and initial is None)
         st = self._state(n_qubits)
         ctx.device_state = st
         if cache is not None:
             st.copy_from(cache)
-            st.apply(comp.prefix)
         elif initial is not None:
             st.upload(initial)
-            st.apply(comp.prefix)
+        # |0...0> is synthesised by the first pass (B200_OP_INIT)
+        init_basis = 0 if cache is None and initial is None else None
+        # a circuit that has to be planned is launched pass by pass while the planner works (see _Streamer); a cached
+        # plan (the same gates by value) goes to the device in one call
+        streamer = _Streamer(st, init_basis) if self.stream_plans and hasattr(st, "apply_piece") else None
+        comp = self._compile(gates, n_qubits, start, getattr(cache, "layout", None) if cache is not None else None,
+                             from_zero=cache is None and initial is None, on_pass=streamer)
+        if streamer is not None and (streamer.ops > 0 or streamer.words > 0):
+            streamer.finish(comp.prefix)
         else:
-            st.apply(comp.prefix, init_basis=0)      # |0...0> is synthesised by the first pass (B200_OP_INIT)
+            st.apply(comp.prefix, init_basis=init_basis)
         self.last_stats = {"n_gates": comp.n_gates, "prefix_passes": comp.prefix.n_passes,
                            "prefix_prims": comp.prefix.n_prims}
         if not comp.rest:

@@ -268,7 +268,7 @@ extern "C" {
 
 const char* b200_last_error(void) { return g_error.c_str(); }
 
-int b200_version(void) { return 102; }   // 102: table variants 17 entries apart, [variant][rho] (tile.cu)
+int b200_version(void) { return 103; }   // 103: b200_apply_program_ex; 102: table variants 17 entries apart (tile.cu)
 
 int b200_device_count(int* out) {
   B200_REQUIRE(out != nullptr, "b200_device_count: null out");
@@ -502,18 +502,18 @@ static int run_simple_op(b200_state* st, const b200_op& op, const double* reals,
 
 int b200_apply_program(b200_state* st, const b200_op* ops, int n_ops, const uint64_t* words, size_t n_words,
                        const double* reals, size_t n_reals) {
+  return b200_apply_program_ex(st, ops, n_ops, words, n_words, reals, n_reals, 0);
+}
+
+// Every op takes what it needs from the host arrays at launch time (a TILE pass travels as kernel parameters, the
+// single-gate kernels take their matrices by value): nothing is uploaded, so a program may be handed over in pieces
+// (B200_APPLY_ASYNC: return without waiting; B200_APPLY_CONTINUE: a further piece of the program whose first piece
+// started the timer) while the host is still planning the rest.
+int b200_apply_program_ex(b200_state* st, const b200_op* ops, int n_ops, const uint64_t* words, size_t n_words,
+                          const double* reals, size_t n_reals, int flags) {
   B200_REQUIRE(st != nullptr, "b200_apply_program: null state");
   B200_REQUIRE(n_ops == 0 || ops != nullptr, "b200_apply_program: null ops");
   B200_CUDA(cudaSetDevice(st->device));
-  bool any_tile = false;
-  for (int i = 0; i < n_ops; ++i) any_tile |= ops[i].kind == B200_OP_TILE;
-  if (any_tile) {
-    if (ensure_capacity(st, n_words, n_reals)) return 1;
-    // The previous program may still be reading the payload buffers.
-    B200_CUDA(cudaStreamSynchronize(st->stream));
-    if (n_words) B200_CUDA(cudaMemcpyAsync(st->d_words, words, sizeof(uint64_t) * n_words, cudaMemcpyHostToDevice, st->stream));
-    if (n_reals) B200_CUDA(cudaMemcpyAsync(st->d_reals, reals, sizeof(double) * n_reals, cudaMemcpyHostToDevice, st->stream));
-  }
   if (st->profiling) {
     while (st->op_events.size() < (size_t)2 * n_ops) {
       cudaEvent_t e;
@@ -522,7 +522,7 @@ int b200_apply_program(b200_state* st, const b200_op* ops, int n_ops, const uint
     }
     st->op_kinds.assign(n_ops, 0);
   }
-  B200_CUDA(cudaEventRecord(st->prog.start, st->stream));
+  if (!(flags & B200_APPLY_CONTINUE)) B200_CUDA(cudaEventRecord(st->prog.start, st->stream));
   uint64_t pending_init = kNoInit;
   for (int i = 0; i < n_ops; ++i) {
     const b200_op& op = ops[i];
@@ -542,7 +542,7 @@ int b200_apply_program(b200_state* st, const b200_op* ops, int n_ops, const uint
       }
     } else if (op.kind == B200_OP_TILE) {
       B200_REQUIRE(op.woff + (uint64_t)op.wlen <= n_words, "TILE descriptor out of range");
-      if (launch_tile_pass(st, st->d_words + op.woff, words + op.woff, op.wlen, st->d_reals, reals, n_reals, pending_init))
+      if (launch_tile_pass(st, words + op.woff, op.wlen, reals, n_reals, pending_init))
         return 1;
       pending_init = kNoInit;
     } else if (op.kind == B200_OP_PERMUTE) {
@@ -555,7 +555,7 @@ int b200_apply_program(b200_state* st, const b200_op* ops, int n_ops, const uint
   }
   B200_CUDA(cudaEventRecord(st->prog.stop, st->stream));
   st->prog.valid = true;
-  B200_CUDA(cudaStreamSynchronize(st->stream));
+  if (!(flags & B200_APPLY_ASYNC)) B200_CUDA(cudaStreamSynchronize(st->stream));
   return 0;
 }
 

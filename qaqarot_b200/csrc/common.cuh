@@ -91,8 +91,8 @@ __host__ __device__ __forceinline__ uint64_t spread(uint64_t k, const BitPositio
 // tile.cu
 // init_index != kNoInit: the pass starts from the basis state |init_index> instead of reading the buffer
 constexpr uint64_t kNoInit = ~0ull;
-int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_desc, int wlen,
-                     const double* d_reals, const double* h_reals, size_t n_reals, uint64_t init_index);
+int launch_tile_pass(b200_state* st, const uint64_t* h_desc, int wlen, const double* h_reals, size_t n_reals,
+                     uint64_t init_index);
 
 // permute.cu
 int launch_permute(b200_state* st, const uint64_t* pairs, int n_pairs);

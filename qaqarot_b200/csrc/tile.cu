@@ -457,7 +457,9 @@ struct PassConst {
   uint32_t pay_lo, pay_len, n_vs, pad1;
   RoundConst rh[kMaxRounds];
   uint4 rec[kMaxGates + 1];
+  uint64_t tb_lo, tb_hi;           // tile bit positions, 8 bits each (descriptor words 1, 2)
   uint32_t vs[kMaxVsWords];        // the per-thread side of the records (copied to shared memory), see below
+  uint64_t fanw[kMaxFanWords];     // fan directory and records (descriptor words [dir_off, rounds_off))
   double pay[kMaxPayload];         // the pass's matrices, phases, tables (the same range of `reals`)
 };
 static_assert(sizeof(PassConst) + 512 <= 32764, "kernel parameters are limited to 32 764 bytes");
@@ -491,8 +493,8 @@ struct TileSmem {
 template <int A, int RB, bool FULL, bool TIMING>
 __global__ void __launch_bounds__(kGroups * (1 << (A - RB)), 1)
 k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMapDev tm, const __grid_constant__ PassConst P,
-       uint64_t n_tiles, uint64_t index_offset, const uint64_t* __restrict__ desc, const double* __restrict__ reals,
-       uint32_t flags, uint64_t init_tile, uint32_t init_local, unsigned long long* __restrict__ phase_cycles) {
+       uint64_t n_tiles, uint64_t index_offset, uint32_t flags, uint64_t init_tile, uint32_t init_local,
+       unsigned long long* __restrict__ phase_cycles) {
   constexpr int R = RB;            // register bits per round (2^R amplitudes per thread)
   constexpr int NT = 1 << (A - R), PER = 1 << R, NTB = A - R;
   constexpr int NWARP_T = (NTB > 5) ? (1 << (NTB - 5)) : 1;
@@ -501,7 +503,7 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
 
   uint32_t tid;                    // (volatile: ptxas otherwise re-reads SR_TID.X inside the record loop)
   asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
-  const uint64_t tb_lo = desc[1], tb_hi = desc[2];
+  const uint64_t tb_lo = P.tb_lo, tb_hi = P.tb_hi;
   const int n_rounds = (int)P.n_rounds, n_fans = (int)P.n_fans;
   const uint32_t dir_off = P.dir_off, rounds_off = P.rounds_off, pay_lo = P.pay_lo, pay_len = P.pay_len;
   // flags bit 1: the state is a basis vector that nobody has written yet -- every tile is all zeros except
@@ -517,8 +519,10 @@ k_tile(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TileMap
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (uint32_t i = tid; i < pay_len; i += blockDim.x) S.pay[i] = reals[pay_lo + i];
-  for (uint32_t i = dir_off + tid; i < rounds_off; i += blockDim.x) S.fanw[i - dir_off] = desc[i];
+  // (the pass arrives entirely as kernel parameters: nothing is uploaded, and a program can be launched pass by pass
+  // while the host is still planning the next one)
+  for (uint32_t i = tid; i < pay_len; i += blockDim.x) S.pay[i] = P.pay[i];
+  for (uint32_t i = tid; i < rounds_off - dir_off; i += blockDim.x) S.fanw[i] = P.fanw[i];
   for (uint32_t i = tid; i < P.n_vs; i += blockDim.x) S.vs[i] = P.vs[i];
   for (uint32_t idx = tid; idx < kSpreadTabs * 64; idx += blockDim.x) {
     uint64_t x = (uint64_t)(idx & 63u) << (6 * (idx >> 6));
@@ -904,7 +908,7 @@ static_assert(sizeof(TileSmem<12, 4>) <= 232448,
               "the 2^12 tile's shared memory exceeds the 227 KB a CTA can have");
 
 template <int A, int RB, bool FULL>
-static int launch(b200_state* st, const PassConst& pc, const uint64_t* d_desc, const double* d_reals, const int* tile, bool init,
+static int launch(b200_state* st, const PassConst& pc, const int* tile, bool init,
                   uint64_t init_tile, uint32_t init_local) {
   constexpr int NT = 1 << (A - RB);
   const size_t smem = sizeof(TileSmem<A, RB>);
@@ -922,7 +926,7 @@ static int launch(b200_state* st, const PassConst& pc, const uint64_t* d_desc, c
   const unsigned grid = (unsigned)(n_tiles < (uint64_t)kSMs ? n_tiles : (uint64_t)kSMs);
   static const bool timing = getenv("B200_TILE_TIMING") != nullptr;
   if (!timing) {
-    k_tile<A, RB, FULL, false><<<grid, kGroups * NT, smem, st->stream>>>(map, tm, pc, n_tiles, st->index_offset, d_desc, d_reals,
+    k_tile<A, RB, FULL, false><<<grid, kGroups * NT, smem, st->stream>>>(map, tm, pc, n_tiles, st->index_offset,
                                                                      init ? 2u : 0u, init_tile, init_local, nullptr);
     st->launches++;
     B200_CUDA(cudaGetLastError());
@@ -932,7 +936,7 @@ static int launch(b200_state* st, const PassConst& pc, const uint64_t* d_desc, c
   unsigned long long* d_cyc = nullptr;
   B200_CUDA(cudaMalloc(&d_cyc, kPhases * sizeof(unsigned long long)));
   B200_CUDA(cudaMemsetAsync(d_cyc, 0, kPhases * sizeof(unsigned long long), st->stream));
-  k_tile<A, RB, FULL, true><<<grid, kGroups * NT, smem, st->stream>>>(map, tm, pc, n_tiles, st->index_offset, d_desc, d_reals,
+  k_tile<A, RB, FULL, true><<<grid, kGroups * NT, smem, st->stream>>>(map, tm, pc, n_tiles, st->index_offset,
                                                                   init ? 2u : 0u, init_tile, init_local, d_cyc);
   st->launches++;
   B200_CUDA(cudaGetLastError());
@@ -951,8 +955,8 @@ static int launch(b200_state* st, const PassConst& pc, const uint64_t* d_desc, c
   return 0;
 }
 
-int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_desc, int wlen,
-                     const double* d_reals, const double* h_reals, size_t n_reals, uint64_t init_index) {
+int launch_tile_pass(b200_state* st, const uint64_t* h_desc, int wlen, const double* h_reals, size_t n_reals,
+                     uint64_t init_index) {
   B200_REQUIRE(wlen >= 5, "TILE descriptor too short");
   const uint64_t h0 = h_desc[0];
   const int A = (int)(h0 & 0xFF), c = (int)((h0 >> 8) & 0xFF), Rd = (int)((h0 >> 16) & 0xFF);
@@ -994,6 +998,9 @@ int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_d
   pc.pay_len = pay_len;
   pc.pad1 = 0;
   for (uint32_t i = 0; i < pay_len; ++i) pc.pay[i] = h_reals[pay_lo + i];
+  pc.tb_lo = h_desc[1];
+  pc.tb_hi = h_desc[2];
+  for (uint64_t i = dir_off; i < rounds_off; ++i) pc.fanw[i - dir_off] = h_desc[i];
   auto in_payload = [&](uint64_t off, uint32_t len) { return off >= pay_lo && off + len <= (uint64_t)pay_lo + pay_len; };
   uint64_t pos = rounds_off, gates = 0;
   uint32_t nvs = 0;               // words of the per-thread stream
@@ -1087,12 +1094,12 @@ int launch_tile_pass(b200_state* st, const uint64_t* d_desc, const uint64_t* h_d
   // twice the warps but a third more rounds per pass -- 210 against 163 ms on the 30-qubit layer circuit, 26.7 against
   // 22.2 ms on the QFT.  The rounds' shared-memory traffic is what a pass pays for, not latency that more warps hide.)
   switch (A) {
-    case 9:  return launch<9, 4, true>(st, pc, d_desc, d_reals, tile, init, init_tile, init_local);
-    case 10: return launch<10, 4, true>(st, pc, d_desc, d_reals, tile, init, init_tile, init_local);
-    case 11: return launch<11, 4, true>(st, pc, d_desc, d_reals, tile, init, init_tile, init_local);
+    case 9:  return launch<9, 4, true>(st, pc, tile, init, init_tile, init_local);
+    case 10: return launch<10, 4, true>(st, pc, tile, init, init_tile, init_local);
+    case 11: return launch<11, 4, true>(st, pc, tile, init, init_tile, init_local);
     // the production tile size also exists without the general target stages (see k_tile)
-    case 12: return full ? launch<12, 4, true>(st, pc, d_desc, d_reals, tile, init, init_tile, init_local)
-                         : launch<12, 4, false>(st, pc, d_desc, d_reals, tile, init, init_tile, init_local);
+    case 12: return full ? launch<12, 4, true>(st, pc, tile, init, init_tile, init_local)
+                         : launch<12, 4, false>(st, pc, tile, init, init_tile, init_local);
     default:
       snprintf(msg, sizeof msg, "TILE descriptor: tile size 2^%d is not built (9..12)", A);
       set_error(msg);

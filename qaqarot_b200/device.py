@@ -79,6 +79,33 @@ class DeviceState:
             self._h, ops, n_ops, words.ctypes.data_as(C.c_void_p), words.size,
             reals.ctypes.data_as(C.c_void_p), reals.size))
 
+    def apply_piece(self, program: Program, op_from: int, op_to: int, words_from: int, reals_from: int,
+                    init_basis: Optional[int] = None, first: bool = True) -> None:
+        """Launch ops [op_from, op_to) of a program that is still being planned, without waiting for the device
+        (b200_apply_program_ex).  Only the pool tails the piece can refer to -- words[words_from:], reals[reals_from:] --
+        are converted; the library reads them at launch time (a pass travels as kernel parameters)."""
+        ops_py = program._ops[op_from:op_to]
+        n = len(ops_py) + (1 if init_basis is not None else 0)
+        if n == 0:
+            return
+        ops = (_lib.Op * n)()
+        k = 0
+        if init_basis is not None:
+            ops[0].kind, ops[0].cmask = _lib.OP_INIT, int(init_basis)
+            k = 1
+        for kind, target, aux, wlen, cmask, woff, roff in ops_py:
+            o = ops[k]
+            o.kind, o.target, o.aux, o.wlen, o.cmask, o.woff, o.roff = kind, target, aux, wlen, cmask, woff, roff
+            k += 1
+        words = np.asarray(program._words[words_from:], dtype=np.uint64)
+        reals = np.asarray(program._reals[reals_from:], dtype=np.float64)
+        # base pointers of the full pools: offsets inside the ops and descriptors are absolute
+        wbase = C.c_void_p(words.ctypes.data - 8 * words_from) if words.size else None
+        rbase = C.c_void_p(reals.ctypes.data - 8 * reals_from) if reals.size else None
+        flags = _lib.APPLY_ASYNC | (0 if first else _lib.APPLY_CONTINUE)
+        _lib.check(self._lib.b200_apply_program_ex(self._h, ops, n, wbase, len(program._words), rbase,
+                                                   len(program._reals), flags))
+
     def last_program_ms(self) -> float:
         ms = C.c_double()
         _lib.check(self._lib.b200_last_program_ms(self._h, C.byref(ms)))

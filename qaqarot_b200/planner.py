@@ -26,7 +26,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass, field
-from typing import Dict, FrozenSet, List, Optional, Sequence, Tuple
+from typing import Callable, Dict, FrozenSet, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -1292,8 +1292,12 @@ def cancelling_layout(prims: Sequence[Prim], n: int) -> List[int]:
 
 
 def plan(prims: Sequence[Prim], n_qubits: int, cfg: PlanConfig = DEFAULT, n_local: Optional[int] = None,
-         initial_pos: Optional[Sequence[int]] = None, free_initial_layout: bool = False) -> Program:
+         initial_pos: Optional[Sequence[int]] = None, free_initial_layout: bool = False,
+         on_pass: Optional[Callable[[Program], None]] = None) -> Program:
     """Primitives of one unitary segment -> op program.
+
+    `on_pass(prog)` is called whenever ops have been appended to `prog` (after every encoded pass): the backend uses
+    it to launch a pass while the next one is still being planned (B200Backend, b200_apply_program_ex).
 
     Single GPU (n_local None): the program leaves every wire on its own index bit (relabelled swaps are paid back
     by at most two PERMUTE passes at the end).  Sharded (n_local < n_qubits): index bits >= n_local are the shard
@@ -1320,6 +1324,8 @@ def plan(prims: Sequence[Prim], n_qubits: int, cfg: PlanConfig = DEFAULT, n_loca
             _emit_single(prog, it, n)
         _emit_restore(prog, norm, n)
         prog.final_pos = list(range(n))
+        if on_pass is not None:
+            on_pass(prog)
         return prog
     a = min(cfg.a, nl)
     if a not in cfg.kernel_tiles:
@@ -1355,11 +1361,15 @@ def plan(prims: Sequence[Prim], n_qubits: int, cfg: PlanConfig = DEFAULT, n_loca
                 if scale == 1.0:
                     raise
         remaining = rest
+        if on_pass is not None:
+            on_pass(prog)
     if sharded:
         prog.n_prims += norm.n_relabelled
     else:
         _emit_restore(prog, norm, n)
         prog.final_pos = list(range(n))
+    if on_pass is not None:
+        on_pass(prog)
     return prog
 
 

@@ -151,6 +151,31 @@ def test_c3_qaoa_28_qubits_energy_against_the_statevector_route():
     assert abs(got - want) < 1e-10
 
 
+@pytest.mark.parametrize("n", [16, 28])
+def test_objective_loop_new_angles_every_call(n):
+    """SURVEY 8(f) rank 1 (vqe.py:67-83): the optimiser rebuilds the ansatz with new angles on every call.  State and
+    work buffers stay on the device, nothing but the energy returns, and a circuit that has to be re-planned is launched
+    pass by pass while the planner is still working (b200_apply_program_ex).  Five random angle vectors: the streamed run
+    against a backend that plans first and launches afterwards, and against the oracle at 16 qubits."""
+    from qaqarot_b200 import workloads as W
+    streamed, plain = B200Backend(), B200Backend()
+    plain.stream_plans = False
+    worst = 0.0
+    for seed in range(5):
+        circ, ham, edges = W.qaoa_maxcut(n, p=4, seed=100 + seed)
+        e1 = circ.run(backend=streamed, hamiltonian=ham)
+        e2 = circ.run(backend=plain, hamiltonian=ham)
+        worst = max(worst, abs(e1 - e2))
+        if n <= 16:
+            psi = _oracle(circ)
+            want = O.expectation([(1.0, [("Z", i), ("Z", j)]) for i, j in edges], psi)
+            assert abs(e1 - want) < 1e-10
+            assert maxabs(circ.run(backend=streamed), psi) <= TOL        # (same angles: the cached plan, one call)
+    streamed.close()
+    plain.close()
+    assert worst <= 1e-12
+
+
 def test_readme_hamiltonian_example(backend):
     """/root/reference/README.md:83-89: Circuit(4).x[:].run(hamiltonian=Z[0] + Z[1]) == -2.0."""
     assert Circuit(4).x[:].run(backend=backend, hamiltonian=1 * Z[0] + 1 * Z[1]) == -2.0
