@@ -1329,7 +1329,11 @@ def plan(prims: Sequence[Prim], n_qubits: int, cfg: PlanConfig = DEFAULT, n_loca
         return prog
     a = min(cfg.a, nl)
     if a not in cfg.kernel_tiles:
-        a = max(t for t in cfg.kernel_tiles if t <= a)
+        fits = [t for t in cfg.kernel_tiles if t <= a]
+        if not fits:
+            raise ValueError(f"a sharded register needs at least {min(cfg.kernel_tiles)} local qubits per GPU for the fused "
+                             f"tile pass, got {nl} (n_qubits = {n}): use fewer ranks or a single B200Backend")
+        a = max(fits)
     r = min(cfg.r, a)
     c = min(cfg.c, a if a == nl else a - 1)       # a tile smaller than the register needs at least one free bit
     remaining = list(norm.items)

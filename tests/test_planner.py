@@ -315,3 +315,14 @@ def test_table_variants_absorb_phases_on_thread_and_fixed_bits():
     ref[bit(5)] *= w[3]
     ref[bit(5) & bit(6)] *= -1
     assert maxabs(st.download(), ref) <= 1e-13
+
+
+def test_sharded_plan_with_too_few_local_qubits_fails_with_a_clear_message():
+    """8 qubits on 4 ranks leave 6 local qubits: no tile size fits (the single-GPU path would fall back to one kernel per
+    gate; a sharded plan cannot)."""
+    from qaqarot_b200 import planner as P
+    from qaqarot_b200.lowering import lower
+    from qaqarot_b200 import Circuit
+    c = Circuit(8).h[:].cx[0, 7]
+    with pytest.raises(ValueError, match="local qubits"):
+        P.plan(lower(list(c.ops), 8).prims, 8, P.DEFAULT, n_local=6)
