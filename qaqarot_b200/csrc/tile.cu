@@ -30,9 +30,15 @@
 // Rounds.  In a round every thread holds 2^R amplitudes in registers: the R *register bits* (local bit
 // positions order[0..R)) enumerate them, the thread index supplies the other A-R local bits through
 // order[R..A).  Non-diagonal gates act on register bits only, so a 2x2 gate is pure register arithmetic
-// (complex128 FMA chains, target position resolved to a compile-time template by a warp-uniform switch);
+// (complex128 FMA chains, target position resolved to a compile-time template by uniform bit tests);
 // controls and phases may involve any bit: register bits become compile-time lane-invariant predicates,
 // thread bits a per-thread predicate, bits outside the tile a per-tile (CTA-uniform) predicate.
+//
+// Dispatch (second half of round 2).  launch_tile_pass decodes the descriptor below ON THE HOST into PassConst -- round
+// headers, one 16-byte record per gate record, the coefficient payload, the fan directory -- and passes it as a kernel
+// parameter: the kernel reads nothing else about the pass (no descriptor upload, a program can be launched pass by
+// pass).  Records and coefficients are read with uniform loads into uniform registers; see PassConst and the notes on
+// the primitives for what that requires of the code.
 //
 // Descriptor (uint64 words, produced by qaqarot_b200/planner.py::encode_pass; `reals` = float64 pool):
 //   D[0] = A | c<<8 | R<<16 | n_rounds<<24 | n_fans<<32 | flags<<40   D[1], D[2] = tile bit positions, 8 bits each
