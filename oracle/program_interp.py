@@ -63,6 +63,18 @@ class OracleState:
         return c
 
     # -- program execution ----------------------------------------------------------------------
+    def apply_piece(self, program, op_from, op_to, words_from, reals_from, init_basis=None, first=True):
+        """Counterpart of DeviceState.apply_piece (b200_apply_program_ex): ops [op_from, op_to) of a program that is still
+        being planned.  Like the library, it may only look at the pool tails the piece refers to: everything below
+        words_from / reals_from is hidden (poisoned) while the piece runs."""
+        from qaqarot_b200.program import Program
+        piece = Program()
+        piece._ops = list(program._ops[op_from:op_to])
+        piece._bytes = list(program._bytes[op_from:op_to])
+        piece._words = [0xDEADBEEFDEADBEEF] * words_from + list(program._words[words_from:])
+        piece._reals = [float("nan")] * reals_from + list(program._reals[reals_from:])
+        self.apply(piece, init_basis=init_basis)
+
     def apply(self, program, init_basis=None):
         if init_basis is not None:
             self.psi[:] = 0.0

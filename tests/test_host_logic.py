@@ -195,3 +195,32 @@ def test_plan_cache_is_keyed_on_gate_values():
     plan_d = be._compiled
     e.run(backend=be, shots=2)
     assert be._compiled is not plan_d
+
+
+def test_newly_planned_circuits_are_launched_pass_by_pass():
+    """a circuit that has to be planned goes to the device in pieces while the planner works
+    (planner.plan's on_pass -> apply_piece); a piece may only read the pool tails appended for it (the interpreter poisons
+    the rest).  Same result as planning first and launching afterwards; the cached plan of a second call goes in one go."""
+    from qaqarot_b200 import workloads as W
+    from helpers import cpu_backend as interp_backend
+    n = 13
+    calls = []
+    streamed, plain = interp_backend(True), interp_backend(True)
+    plain.stream_plans = False
+    st = streamed._state(n)
+    orig = st.apply_piece
+
+    def spy(*a, **kw):
+        calls.append(a[1:3])
+        return orig(*a, **kw)
+    st.apply_piece = spy
+    for seed in range(3):
+        circ, ham, _ = W.qaoa_maxcut(n, p=3, seed=seed)
+        a = circ.run(backend=streamed)
+        b = circ.run(backend=plain)
+        assert np.abs(a - b).max() <= 1e-15
+        n_pieces = len(calls)
+        assert n_pieces >= 2 and calls[0][0] == 0 and all(x[1] == y[0] for x, y in zip(calls, calls[1:]))
+        assert abs(circ.run(backend=streamed, hamiltonian=ham) - circ.run(backend=plain, hamiltonian=ham)) <= 1e-12
+        assert len(calls) == n_pieces            # same gates by value: the cached plan, one apply()
+        del calls[:]
