@@ -62,7 +62,7 @@ typedef struct b200_op {
 
 const char* b200_last_error(void);
 int b200_device_count(int* out);
-int b200_version(void);                 /* 103; bumped whenever the TILE descriptor format changes */
+int b200_version(void);                 /* 104; bumped whenever the TILE descriptor format changes */
 
 /* ---- state lifetime (replaces _NumPyBackendContext.__init__/prepare, numpy_backend.py:36-62) ---- */
 
@@ -132,6 +132,10 @@ int b200_sample(b200_state* st, const int32_t* order, int m, const double* unifo
    with bit = 1; qubit < 0: sums[2g] is the whole group.                                                   */
 int b200_cond_probs(b200_state* st, uint64_t fixed_mask, int qubit, const uint64_t* group_bits, int n_groups,
                     double* sums);
+/* Marginal distribution of the low k index bits (8 <= k <= 13): table[v] = sum of |amp[i]|^2 over the i with
+   i mod 2^k = v, from one contiguous read of the state.  The first levels of the descent when the first measured
+   qubits sit on index bits 0..k-1 (b200_sample uses it itself; sharded callers add the per-shard tables).     */
+int b200_marginal_low(b200_state* st, int k, double* table);
 
 /* ---- Pauli expectation (replaces Expr.to_matrix + sparse_expectation, pauli.py:893-935,
         vqe.py:355-366).  One group = all terms sharing the same X/Y flip mask `xmask`:

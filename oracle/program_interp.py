@@ -54,6 +54,13 @@ class OracleState:
             return out
         return res
 
+    MARGINAL_LOW_BITS = (8, 13)
+
+    def marginal_low(self, k):
+        """Counterpart of b200_marginal_low: table[v] = sum |amp[i]|^2 over i mod 2^k = v."""
+        p = self.psi.real ** 2 + self.psi.imag ** 2
+        return p.reshape(-1, 1 << k).sum(axis=0)
+
     def copy_from(self, other):
         self.psi[:] = other.psi
 

@@ -14,7 +14,7 @@ from typing import List, Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libb200sv.so")
-ABI_VERSION = 103            # b200_version() of the library this planner's TILE descriptors are written for
+ABI_VERSION = 104            # b200_version() of the library this planner's TILE descriptors are written for
 SOURCES = ["b200sv.cu", "sample.cu", "tile.cu", "permute.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -71,6 +71,7 @@ _SIGNATURES = {
     "b200_expect_group": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                     _P(C.c_double), _P(C.c_double)]),
     "b200_cond_probs": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "b200_marginal_low": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "b200_state_set_index_offset": (C.c_int, [C.c_void_p, C.c_uint64]),
     "b200_sync": (C.c_int, [C.c_void_p]),
     "b200_state_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -268,7 +268,7 @@ extern "C" {
 
 const char* b200_last_error(void) { return g_error.c_str(); }
 
-int b200_version(void) { return 103; }   // 103: b200_apply_program_ex; 102: table variants 17 entries apart (tile.cu)
+int b200_version(void) { return 104; }   // 104: b200_marginal_low; 103: b200_apply_program_ex; 102: table variants 17 entries apart (tile.cu)
 
 int b200_device_count(int* out) {
   B200_REQUIRE(out != nullptr, "b200_device_count: null out");

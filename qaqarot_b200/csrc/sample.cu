@@ -79,6 +79,46 @@ __global__ void k_group_finish(const double* __restrict__ partial, int n_groups,
   out[2 * (size_t)g + 1] = t1;
 }
 
+// Marginal distribution of the LOW k index bits: table[v] = sum of |amp[i]|^2 over the i whose low k bits are v.
+// This is what the first levels of a descent need when the first measured qubits sit on index bits 0..k-1 (m[:] on a
+// state in its natural layout) -- and the case in which k_cond_prob is at its worst: its groups then are strided
+// subsets (one 16-byte amplitude every 2^k * 16 bytes), a quarter of the DRAM efficiency of a contiguous read or
+// less; at 36 qubits on 8 GPUs the descent spent ~0.4 s that way.  Here a block reads a CONTIGUOUS slab, thread t the
+// amplitudes base + t + 256 s: the bin of an amplitude is its index mod 2^k, so thread t only ever touches the bins
+// congruent to t mod 256 -- private to it, no atomics, a fixed summation order, one bank per lane.
+constexpr int kMargThreads = 256;
+constexpr int kMargMaxBits = 13;        // 2^13 bins of 8 bytes = 64 KB of shared memory per block
+
+__global__ void __launch_bounds__(kMargThreads)
+k_marginal_low(const c128* __restrict__ amp, uint64_t per_block, int k, double* __restrict__ partial) {
+  extern __shared__ double bins[];
+  const uint32_t nb = 1u << k, mask = nb - 1u;
+  for (uint32_t i = threadIdx.x; i < nb; i += kMargThreads) bins[i] = 0.0;
+  __syncthreads();
+  const c128* __restrict__ p = amp + (uint64_t)blockIdx.x * per_block;     // per_block is a multiple of 1024
+  for (uint64_t off = threadIdx.x; off < per_block; off += 4 * kMargThreads) {
+    c128 a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = __ldcs(p + off + (uint64_t)u * kMargThreads);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t b = (uint32_t)(off + (uint64_t)u * kMargThreads) & mask;    // (the slab starts on a multiple of 2^k)
+      bins[b] += a[u].x * a[u].x + a[u].y * a[u].y;
+    }
+  }
+  __syncthreads();
+  double* __restrict__ out = partial + (size_t)blockIdx.x * nb;
+  for (uint32_t i = threadIdx.x; i < nb; i += kMargThreads) out[i] = bins[i];
+}
+
+__global__ void k_marginal_finish(const double* __restrict__ partial, int n_blocks, uint32_t nb, double* __restrict__ table) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nb) return;
+  double t = 0.0;
+  for (int b = 0; b < n_blocks; ++b) t += partial[(size_t)b * nb + v];
+  table[v] = t;
+}
+
 // The three device arrays of one reduction live in one grow-only allocation owned by the state (a descent makes up
 // to 64 reductions; allocating and freeing per level cost three cudaMalloc / cudaFree pairs each, and cudaFree
 // synchronises the device).
@@ -145,6 +185,39 @@ static int cond_probs(b200_state* st, uint64_t fixed_mask, int qubit, const uint
   return 0;
 }
 
+static int marginal_low(b200_state* st, int k, double* table) {
+  const uint32_t nb = 1u << k;
+  // slabs: a multiple of 2^k and of 4 * 256 amplitudes each, at most 512 of them
+  uint64_t per_block = std::max<uint64_t>((uint64_t)nb, 4ull * kMargThreads);
+  while (st->dim / per_block > 512) per_block <<= 1;
+  const int n_blocks = (int)(st->dim / per_block);
+  const size_t sz_partial = sizeof(double) * (size_t)n_blocks * nb, sz_table = sizeof(double) * nb;
+  unsigned char* base = nullptr;
+  if (sampler_scratch(st, sz_partial + sz_table, &base)) return 1;
+  double* d_partial = reinterpret_cast<double*>(base);
+  double* d_table = reinterpret_cast<double*>(base + sz_partial);
+  static bool configured[64] = {};
+  if (!configured[st->device & 63]) {
+    B200_CUDA(cudaFuncSetAttribute(k_marginal_low, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) << kMargMaxBits)));
+    configured[st->device & 63] = true;
+  }
+  k_marginal_low<<<n_blocks, kMargThreads, sizeof(double) * nb, st->stream>>>(st->amp, per_block, k, d_partial);
+  B200_CUDA(cudaGetLastError());
+  k_marginal_finish<<<(nb + 255) / 256, 256, 0, st->stream>>>(d_partial, n_blocks, nb, d_table);
+  B200_CUDA(cudaGetLastError());
+  st->launches += 2;
+  B200_CUDA(cudaMemcpyAsync(table, d_table, sz_table, cudaMemcpyDeviceToHost, st->stream));
+  B200_CUDA(cudaStreamSynchronize(st->stream));
+  return 0;
+}
+
+extern "C" int b200_marginal_low(b200_state* st, int k, double* table) {
+  B200_REQUIRE(st != nullptr && table != nullptr, "b200_marginal_low: null argument");
+  B200_REQUIRE(k >= 8 && k <= kMargMaxBits && k <= st->n - 2, "b200_marginal_low: 8..13 low bits of a state with at least 2 more");
+  B200_CUDA(cudaSetDevice(st->device));
+  return marginal_low(st, k, table);
+}
+
 extern "C" int b200_cond_probs(b200_state* st, uint64_t fixed_mask, int qubit, const uint64_t* group_bits,
                                int n_groups, double* sums) {
   B200_REQUIRE(st != nullptr && group_bits != nullptr && sums != nullptr, "b200_cond_probs: null argument");
@@ -178,7 +251,47 @@ extern "C" int b200_sample(b200_state* st, const int32_t* order, int m, const do
   // conditionals of the levels above it are sums of its entries.  Level by level, each of the first
   // log2(shots) levels would be a full read of the state.
   int j0 = 0;
+  // ... and when the first K measured qubits are exactly the index bits 0..K-1 (in any order), K up to 13, the table comes
+  // from one CONTIGUOUS read of the state (k_marginal_low) instead of 2^(K-1) strided groups.
   {
+    int K = 0;
+    uint64_t seen = 0;
+    for (int t = 0, kk = 0; t < m && t < kMargMaxBits && !((seen >> order[t]) & 1ull); ++t) {
+      seen |= 1ull << order[t];
+      ++kk;
+      if (seen == (1ull << kk) - 1ull) K = kk;          // the first kk qubits are the low kk bits
+    }
+    if (K >= 11 && K <= st->n - 2) {
+      std::vector<double> table((size_t)1 << K);
+      if (marginal_low(st, K, table.data())) return 1;
+      std::vector<std::vector<double>> node(K + 1);
+      node[K].resize((size_t)1 << K);
+      for (uint32_t p = 0; p < (1u << K); ++p) {         // bit t of p = outcome of order[t] = index bit order[t]
+        uint32_t v = 0;
+        for (int t = 0; t < K; ++t) v |= ((p >> t) & 1u) << order[t];
+        node[K][p] = table[v];
+      }
+      for (int j = K - 1; j >= 0; --j) {
+        node[j].resize((size_t)1 << j);
+        for (int p = 0; p < (1 << j); ++p) node[j][p] = node[j + 1][p] + node[j + 1][p | (1 << j)];
+      }
+      for (int s = 0; s < n_shots; ++s) {
+        int p = 0;
+        for (int j = 0; j < K; ++j) {
+          const double s0 = node[j + 1][p], s1 = node[j + 1][p | (1 << j)];
+          const double p0 = s0 / (s0 + s1);
+          if (!(uniforms[(size_t)s * m + j] < p0)) {
+            p |= 1 << j;
+            out_bits[s] |= 1ull << j;
+            prefix[s] |= 1ull << order[j];
+          }
+        }
+      }
+      fixed_mask = (1ull << K) - 1ull;
+      j0 = K;
+    }
+  }
+  if (j0 == 0) {
     int K = 0;
     uint64_t seen = 0;
     while (K < m && K < 10 && !((seen >> order[K]) & 1ull)) seen |= 1ull << order[K++];

@@ -216,6 +216,14 @@ class DeviceState:
         """Pairs [start, start + count): amp[i | lbit = 1 - my_bit] <-> peer[i | lbit = my_bit] (synchronous)."""
         _lib.check(self._lib.b200_peer_swap(self._h, C.c_void_p(peer_ptr), lbit, my_bit, start, count))
 
+    MARGINAL_LOW_BITS = (8, 13)        # b200_marginal_low accepts this many low index bits
+
+    def marginal_low(self, k: int) -> np.ndarray:
+        """table[v] = sum |amp[i]|^2 over i mod 2^k = v, one contiguous read of the state (8 <= k <= 13)."""
+        out = np.zeros(1 << k, dtype=np.float64)
+        _lib.check(self._lib.b200_marginal_low(self._h, k, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def cond_probs(self, fixed_mask: int, qubit: int, group_bits: np.ndarray) -> np.ndarray:
         """(n_groups, 2): sum |amp|^2 of every group with bit `qubit` = 0 / 1 (qubit < 0: whole group, 0)."""
         gb = np.ascontiguousarray(group_bits, dtype=np.uint64)

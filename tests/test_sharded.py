@@ -88,6 +88,23 @@ def _worker(rank, world, port, errors):
         want = oracle(circ, shots=100)
         random.seed(4)
         assert circ.run(backend=be, shots=100) == want
+        # 2b. a register large enough for the contiguous low-bit marginal (b200_marginal_low: the first 11+ measured wires
+        # on the local index bits 0..10+): same Counter, and the table really came from that call
+        n2 = 15
+        circ = W.random_layers(n2, 3).m[:]
+        random.seed(6)
+        want = oracle(circ, shots=150)
+        random.seed(6)
+        ctx = circ.run(backend=be, shots=150, returns="_inner_ctx")
+        assert ctx.shots_result == want
+        local = ctx.device_state.st
+        calls = []
+        orig = local.marginal_low
+        local.marginal_low = lambda k: (calls.append(k), orig(k))[1]
+        random.seed(6)
+        assert circ.run(backend=be, shots=150) == want
+        if world == 2:            # (with more ranks the wires that came home may have displaced one of the low ones)
+            assert calls and calls[0] >= 11, calls
         # 3. mid-circuit measurement and reset on a global wire (trajectory path: prob_zero / collapse)
         circ = Circuit(n).h[:].cx[0, 8].m[8].h[8].reset[7].rx(0.3)[7].m[:]
         random.seed(5)
