@@ -90,7 +90,7 @@ def _worker(rank, world, port, errors):
         assert circ.run(backend=be, shots=100) == want
         # 2b. a register large enough for the contiguous low-bit marginal (b200_marginal_low: the first 11+ measured wires
         # on the local index bits 0..10+): same Counter, and the table really came from that call
-        n2 = 14
+        n2 = 15
         circ = W.random_layers(n2, 3).m[:]
         random.seed(6)
         want = oracle(circ, shots=150)
