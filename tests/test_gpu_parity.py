@@ -176,6 +176,21 @@ def test_objective_loop_new_angles_every_call(n):
     assert worst <= 1e-12
 
 
+def test_runs_are_bit_reproducible():
+    """The same program three times on 2^24 amplitudes: bit-identical statevectors.  (compute-sanitizer is not available on
+    the GPU pool; a race between the TMA pipeline, the group barriers and the register tile would show up here as a
+    difference in some run.)  Layers + QFT: layer records, tables with variants, fans."""
+    from qaqarot_b200 import workloads as W
+    n = 24
+    be = B200Backend()
+    for circ in (W.random_layers(n, 10), W.qft(n, 987654321)):
+        first = circ.run(backend=be).copy()
+        for _ in range(2):
+            be._compiled = None
+            assert np.array_equal(circ.run(backend=be), first)
+    be.close()
+
+
 def test_readme_hamiltonian_example(backend):
     """/root/reference/README.md:83-89: Circuit(4).x[:].run(hamiltonian=Z[0] + Z[1]) == -2.0."""
     assert Circuit(4).x[:].run(backend=backend, hamiltonian=1 * Z[0] + 1 * Z[1]) == -2.0
