@@ -64,6 +64,9 @@ class PlanConfig:
     kernel_tiles: Tuple[int, ...] = (9, 10, 11, 12)       # tile sizes csrc/tile.cu instantiates (r = 4)
     bank_pairs: bool = True   # keep both local bits of a shared-memory bank pair (0,3), (1,4), (2,5) out of one
                               # round's register set when the gates can wait for the next round (see _thread_order)
+    exact_rotations: bool = False   # every rotation as three exact shears (no cosine factors left for the tables): then
+                              # every table / fan / phase entry of a circuit of rotations and phase gates is a constant
+                              # times exp(i a.theta), which is what param_replay.ParamModel relies on
     shears: bool = True       # 1-qubit gates as phase . rotation by three shears . phase (split_shears), and
                               # CX as H . CZ . H
 
@@ -153,6 +156,9 @@ def rotation_matrix(theta: float) -> np.ndarray:
     return np.array([c, -sn, sn, c], dtype=complex)
 
 
+_EXACT_SHEARS = False      # set by plan() from PlanConfig.exact_rotations for the duration of one call
+
+
 def shear_params(theta: float, exact: bool = False) -> Tuple[float, float, float, float, float]:
     """(z, x, y, c_all, c_bit): R(theta), |theta| <= pi/2, as the in-place updates of a LAYER record (csrc/tile.cu)
 
@@ -163,7 +169,7 @@ def shear_params(theta: float, exact: bool = False) -> Tuple[float, float, float
     c = cos(theta): c_all = c, c_bit = 1 + t^2, both within [1/2, 2].  Larger angles, or `exact`: the three shears of
     the lifting scheme, z = y = -tan(theta / 2), x = sin(theta), c_all = c_bit = 1 at the price of the third update
     (cheaper than two updates and a table when the record has no other use for a table)."""
-    if not exact and abs(theta) <= math.pi / 4 + 1e-15:
+    if not exact and not _EXACT_SHEARS and abs(theta) <= math.pi / 4 + 1e-15:
         t = math.tan(theta)
         return -t, t / (1.0 + t * t), 0.0, 1.0 / math.sqrt(1.0 + t * t), 1.0 + t * t
     z = -math.tan(theta / 2.0)
@@ -213,7 +219,8 @@ def split_rotation(m, allow_anti: bool = True) -> Optional[Tuple[complex, comple
         dr = -_unit(b) / g
         # the phases are read off the LARGE entries (those of small ones are only known to ~eps / |entry|)
         dl = _unit(d) / (g * dr) if abs(a) >= abs(c) else _unit(c) / g
-    anti = allow_anti and abs(theta) > math.pi / 4 + 1e-15
+    # (exact rotations need no |theta| <= pi/4: one branch of the plan less that moves with the angles)
+    anti = allow_anti and not _EXACT_SHEARS and abs(theta) > math.pi / 4 + 1e-15
     if anti:                                       # R(theta) = +-A . R(theta -+ pi/2)
         if theta < 0:
             g = -g
@@ -1294,6 +1301,18 @@ def cancelling_layout(prims: Sequence[Prim], n: int) -> List[int]:
 def plan(prims: Sequence[Prim], n_qubits: int, cfg: PlanConfig = DEFAULT, n_local: Optional[int] = None,
          initial_pos: Optional[Sequence[int]] = None, free_initial_layout: bool = False,
          on_pass: Optional[Callable[[Program], None]] = None) -> Program:
+    """See _plan (this wrapper only scopes PlanConfig.exact_rotations)."""
+    global _EXACT_SHEARS
+    saved, _EXACT_SHEARS = _EXACT_SHEARS, bool(cfg.exact_rotations)
+    try:
+        return _plan(prims, n_qubits, cfg, n_local, initial_pos, free_initial_layout, on_pass)
+    finally:
+        _EXACT_SHEARS = saved
+
+
+def _plan(prims: Sequence[Prim], n_qubits: int, cfg: PlanConfig = DEFAULT, n_local: Optional[int] = None,
+          initial_pos: Optional[Sequence[int]] = None, free_initial_layout: bool = False,
+          on_pass: Optional[Callable[[Program], None]] = None) -> Program:
     """Primitives of one unitary segment -> op program.
 
     `on_pass(prog)` is called whenever ops have been appended to `prog` (after every encoded pass): the backend uses

@@ -154,12 +154,14 @@ def test_c3_qaoa_28_qubits_energy_against_the_statevector_route():
 @pytest.mark.parametrize("n", [16, 28])
 def test_objective_loop_new_angles_every_call(n):
     """SURVEY 8(f) rank 1 (vqe.py:67-83): the optimiser rebuilds the ansatz with new angles on every call.  State and
-    work buffers stay on the device, nothing but the energy returns, and a circuit that has to be re-planned is launched
-    pass by pass while the planner is still working (b200_apply_program_ex).  Five random angle vectors: the streamed run
-    against a backend that plans first and launches afterwards, and against the oracle at 16 qubits."""
+    work buffers stay on the device, nothing but the energy returns; the first call is launched pass by pass while the
+    planner is still working (b200_apply_program_ex), the later ones at once from param_replay's model of the planner,
+    confirmed by the real plan made while the device runs.  Five random angle vectors against a backend that plans first
+    and launches afterwards, and against the oracle at 16 qubits."""
     from qaqarot_b200 import workloads as W
     streamed, plain = B200Backend(), B200Backend()
     plain.stream_plans = False
+    plain.param_replay = False
     worst = 0.0
     for seed in range(5):
         circ, ham, edges = W.qaoa_maxcut(n, p=4, seed=100 + seed)
@@ -171,6 +173,9 @@ def test_objective_loop_new_angles_every_call(n):
             want = O.expectation([(1.0, [("Z", i), ("Z", j)]) for i, j in edges], psi)
             assert abs(e1 - want) < 1e-10
             assert maxabs(circ.run(backend=streamed), psi) <= TOL        # (same angles: the cached plan, one call)
+    # from the second call on the circuit was launched with the payload param_replay's model of the planner predicted,
+    # and the real plan confirmed every one of them
+    assert streamed.replay_stats == {"built": 1, "hits": 4, "misses": 0, "unmodelable": 0}
     streamed.close()
     plain.close()
     assert worst <= 1e-12

@@ -207,6 +207,7 @@ def test_newly_planned_circuits_are_launched_pass_by_pass():
     calls = []
     streamed, plain = interp_backend(True), interp_backend(True)
     plain.stream_plans = False
+    streamed.param_replay = plain.param_replay = False      # (the speculative launch has its own test below)
     st = streamed._state(n)
     orig = st.apply_piece
 
@@ -224,3 +225,37 @@ def test_newly_planned_circuits_are_launched_pass_by_pass():
         assert abs(circ.run(backend=streamed, hamiltonian=ham) - circ.run(backend=plain, hamiltonian=ham)) <= 1e-12
         assert len(calls) == n_pieces            # same gates by value: the cached plan, one apply()
         del calls[:]
+
+
+def test_objective_loop_launches_from_the_planner_model_and_checks_it():
+    """SURVEY 8(f) rank 1, param_replay: the second call with the same gate structure and other angles builds a model of
+    the planner's payload; from then on the circuit is launched with the predicted payload before it is planned, and the
+    real plan only confirms it.  Energies against the oracle; a model that predicts wrongly costs a second run, never a
+    wrong answer."""
+    from qaqarot_b200 import workloads as W
+    from qaqarot_b200 import param_replay as R
+    from helpers import cpu_backend
+    from oracle import sv_oracle as O
+    n = 12
+    be = cpu_backend(True)
+    for seed in range(5):
+        circ, ham, edges = W.qaoa_maxcut(n, p=3, seed=seed)
+        psi = O.OracleBackend().run(circ.ops, n)
+        want = O.expectation([(1.0, [("Z", i), ("Z", j)]) for i, j in edges], psi)
+        assert abs(circ.run(backend=be, hamiltonian=ham) - want) < 1e-10
+        assert maxabs(circ.run(backend=be), psi) <= 1e-12               # (same angles: the cached plan)
+    assert be.replay_stats == {"built": 1, "hits": 4, "misses": 0, "unmodelable": 0}
+    # a model that is wrong: the real plan disagrees, the circuit runs again, the model is dropped
+    (model,) = [m for m in be._models.values() if m is not None]
+    model.E0_live = model.E0_live * np.exp(0.3j)
+    circ, ham, edges = W.qaoa_maxcut(n, p=3, seed=77)
+    psi = O.OracleBackend().run(circ.ops, n)
+    assert maxabs(circ.run(backend=be), psi) <= 1e-12
+    assert be.replay_stats["misses"] == 1 and all(m is None for m in be._models.values())
+    # a structure whose payload is not of the model's form (a general 2x2 that moves with the angle) is left alone
+    from qaqarot_b200 import Circuit
+    be2 = cpu_backend(True)
+    for th in (0.3, 0.9, 1.4):
+        c = Circuit(n).h[:].u(th, 0.2, 0.5)[3].cx[3, 4].rx(th)[:]
+        assert maxabs(c.run(backend=be2), O.OracleBackend().run(c.ops, n)) <= 1e-12
+    assert be2.replay_stats["hits"] == 0
