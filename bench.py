@@ -447,14 +447,14 @@ def run_extras(be, args) -> dict:
     r = measure_resident(be, circ, n, steps, warmup)
     roof = r["roofline"]
     # the objective loop (vqe.py:67-83): a NEW angle vector every call, nothing but the energy returns.  First with the
-    # speculative launch from the planner model off (every call plans, then launches pass by pass), then with it on (two
-    # calls to build the model, untimed like any warm-up).
+    # speculative launch from the planner model off (every call plans, then launches pass by pass), then with it on (three
+    # calls until the model exists, untimed like any warm-up).
     loops = {}
     for replay in (False, True):
         be.param_replay = replay
         be._models.clear()
         be._last_key = None
-        for seed in (900, 901):
+        for seed in (900, 901, 902):
             c2, h2, _ = W.qaoa_maxcut(n, seed=seed)
             c2.run(backend=be, hamiltonian=h2)
         t0 = time.perf_counter()

@@ -210,6 +210,7 @@ class B200Backend(_Base):
         self._models: Dict[Any, Any] = {}    # structure key -> ParamModel, or None when the structure is not modelable
         self._last_key = None
         self._last_angles = None
+        self._repeats = 0
         self.replay_stats = {"built": 0, "hits": 0, "misses": 0, "unmodelable": 0}
         self._work = None                    # reusable work state
         self._compiled: Optional[_Compiled] = None
@@ -262,8 +263,8 @@ class B200Backend(_Base):
 
     # -- objective loops: speculative launch from a model of the planner (param_replay.py) -------------------
     def _replay_model(self, gates, n_qubits: int):
-        """The ParamModel of this gate structure, built when the structure shows up a second time in a row with other
-        angles; None when there is none (yet) or the structure is not modelable."""
+        """The ParamModel of this gate structure, built when the structure shows up for the third time in a row with
+        other angles; None when there is none (yet) or the structure is not modelable."""
         from . import param_replay as R
         key = R.structure_key(gates, n_qubits)
         angles = R.angle_values(gates)
@@ -272,6 +273,11 @@ class B200Backend(_Base):
         if key in self._models:
             return self._models[key], angles
         if key != last_key or angles.size == 0 or np.array_equal(angles, last_angles):
+            self._repeats = 0
+            return None, angles
+        # the model costs one plan per distinct angle: only a loop pays that back, so wait for the third call in a row
+        self._repeats += 1
+        if self._repeats < 2:
             return None, angles
         planner = self._planner_exact
 

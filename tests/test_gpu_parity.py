@@ -173,9 +173,9 @@ def test_objective_loop_new_angles_every_call(n):
             want = O.expectation([(1.0, [("Z", i), ("Z", j)]) for i, j in edges], psi)
             assert abs(e1 - want) < 1e-10
             assert maxabs(circ.run(backend=streamed), psi) <= TOL        # (same angles: the cached plan, one call)
-    # from the second call on the circuit was launched with the payload param_replay's model of the planner predicted,
+    # from the third call on the circuit was launched with the payload param_replay's model of the planner predicted,
     # and the real plan confirmed every one of them
-    assert streamed.replay_stats == {"built": 1, "hits": 4, "misses": 0, "unmodelable": 0}
+    assert streamed.replay_stats == {"built": 1, "hits": 3, "misses": 0, "unmodelable": 0}
     streamed.close()
     plain.close()
     assert worst <= 1e-12
