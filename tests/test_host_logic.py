@@ -4,6 +4,7 @@ The device is replaced by oracle/program_interp.OracleState, an independent nump
 program, so these tests pin everything above the C ABI against the reference fixtures without a GPU.
 """
 import random
+import sys
 import warnings
 from collections import Counter
 
@@ -259,3 +260,33 @@ def test_objective_loop_launches_from_the_planner_model_and_checks_it():
         c = Circuit(n).h[:].u(th, 0.2, 0.5)[3].cx[3, 4].rx(th)[:]
         assert maxabs(c.run(backend=be2), O.OracleBackend().run(c.ops, n)) <= 1e-12
     assert be2.replay_stats["hits"] == 0
+
+
+@pytest.mark.reference
+def test_objective_loop_with_blueqats_own_qaoa_ansatz():
+    """The reference's own call path (vqe.py:130-144 QaoaAnsatz.get_circuit, rebuilt for every angle vector): genuine
+    blueqat gate objects go through structure_key / with_angles (Operation.create), the model is built on the third call
+    and confirmed on every later one; statevectors against blueqat's numpy backend."""
+    import warnings
+    from conftest import REFERENCE
+    sys.path.insert(0, REFERENCE)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            from blueqat import vqe
+            from blueqat.pauli import Z as BZ
+    finally:
+        sys.path.remove(REFERENCE)
+    from helpers import cpu_backend
+    n = 12
+    ham = sum((BZ[i] * BZ[(i + 1) % n] for i in range(1, n)), BZ[0] * BZ[1])
+    ansatz = vqe.QaoaAnsatz(ham, 2)
+    be = cpu_backend(True)
+    rng = np.random.default_rng(3)
+    for _ in range(5):
+        circ = ansatz.get_circuit(rng.uniform(0, 1, 4))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = circ.run(backend="numpy")
+        assert maxabs(circ.run(backend=be), want) <= 1e-12
+    assert be.replay_stats["built"] == 1 and be.replay_stats["hits"] == 3 and be.replay_stats["misses"] == 0
