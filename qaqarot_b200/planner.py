@@ -125,9 +125,10 @@ _HM = np.array([1, 1, 1, -1], dtype=complex) / np.sqrt(2.0)
 
 
 def _mul(a: np.ndarray, b: np.ndarray) -> np.ndarray:
-    """Row-major 2x2 product a @ b."""
-    return np.array([a[0] * b[0] + a[1] * b[2], a[0] * b[1] + a[1] * b[3],
-                     a[2] * b[0] + a[3] * b[2], a[2] * b[1] + a[3] * b[3]], dtype=complex)
+    """Row-major 2x2 product a @ b (in Python complex arithmetic: numpy scalars cost ten times as much per operation)."""
+    a0, a1, a2, a3 = a.tolist()
+    b0, b1, b2, b3 = b.tolist()
+    return np.array([a0 * b0 + a1 * b2, a0 * b1 + a1 * b3, a2 * b0 + a3 * b2, a2 * b1 + a3 * b3], dtype=complex)
 
 
 def _is_diag(m) -> bool:
@@ -200,8 +201,10 @@ def split_rotation(m, allow_anti: bool = True) -> Optional[Tuple[complex, comple
     conjugated by it (emit_conjugated), and the next gate on the wire absorbs it.  A real rotation keeps dl = dr = 1; a
     real reflection (H) is a rotation times Z.
     Returns (g, dl, theta, dr, anti), or None when the pieces do not reproduce `m` to rounding (not unitary)."""
-    a, b, c, d = (complex(v) for v in np.asarray(m).reshape(4))          # (plain Python arithmetic: this runs once
-    if not all(math.isfinite(v.real) and math.isfinite(v.imag) for v in (a, b, c, d)):     # per gate of a circuit)
+    a, b, c, d = np.asarray(m, dtype=complex).reshape(4).tolist()         # (plain Python arithmetic: this runs once
+    isf = math.isfinite                                                  # per gate of a circuit)
+    if not (isf(a.real) and isf(a.imag) and isf(b.real) and isf(b.imag) and isf(c.real) and isf(c.imag)
+            and isf(d.real) and isf(d.imag)):
         return None
     if c == 0 or b == 0:
         return None                               # diagonal matrices never get here; anything else is not unitary
@@ -225,7 +228,9 @@ def split_rotation(m, allow_anti: bool = True) -> Optional[Tuple[complex, comple
         if theta < 0:
             g = -g
         theta -= math.copysign(math.pi / 2, theta)
-    r00, r01, r10, r11 = (v.real for v in rotation_matrix(theta))
+    r00 = r11 = math.cos(theta)                      # (rotation_matrix(theta), without the array)
+    r10 = math.sin(theta)
+    r01 = -r10
     if anti:
         r00, r01, r10, r11 = -r10, -r11, r00, r01
     err = max(abs(g * r00 - a), abs(g * r01 * dr - b), abs(g * dl * r10 - c), abs(g * dl * r11 * dr - d))
