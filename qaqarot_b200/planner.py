@@ -741,6 +741,14 @@ def build_pass(remaining: List[Item], n: int, a: int, r: int, c: int, cfg: PlanC
     payload = 0
     fan_words = 0
     limit = min(len(remaining), cfg.scan_limit)
+    # per item, once per pass: (schedulable, payload bound, fan with entries, fan words, cost, mat / x, plain fan)
+    info = []
+    for it in remaining[:limit]:
+        kind = it.kind
+        is_fan = kind == "fan" and bool(it.entries)
+        info.append((kind not in ("swap", "perm", "exchange"), int(_payload(it, a, r) * pay_scale), is_fan,
+                     3 + len(it.entries) if is_fan else (1 if kind in ("phase", "fan") else 0), _cost(it),
+                     kind in ("mat", "x"), kind == "fan" and not it.entries))
     for _ in range(cfg.max_rounds):
         reg: List[int] = []
         picked: List[int] = []
@@ -748,27 +756,28 @@ def build_pass(remaining: List[Item], n: int, a: int, r: int, c: int, cfg: PlanC
         skipped_dg: set = set()
         nd_left: Dict[int, int] = {}               # wire -> non-diagonal gates on it still to be scheduled
         for idx in range(limit):
-            if not done[idx] and remaining[idx].kind in ("mat", "x"):
-                nd_left[remaining[idx].t] = nd_left.get(remaining[idx].t, 0) + 1
+            if not done[idx] and info[idx][5]:
+                t = remaining[idx].t
+                nd_left[t] = nd_left.get(t, 0) + 1
         for idx in range(limit):
             if done[idx]:
                 continue
             it = remaining[idx]
-            ok = it.kind not in ("swap", "perm", "exchange") and not _conflict(it, skipped_nd, skipped_dg)
-            pay = int(_payload(it, a, r) * pay_scale)
-            is_fan = it.kind == "fan" and bool(it.entries)
-            fw = 3 + len(it.entries) if is_fan else (1 if it.kind in ("phase", "fan") else 0)
+            sched, pay, is_fan, fw, it_cost, is_nd_kind, plain_fan = info[idx]
+            nd, dg = it.nd, it.dg
+            # (_conflict: a gate cannot pass a skipped one it does not commute with)
+            ok = sched and nd.isdisjoint(skipped_nd) and nd.isdisjoint(skipped_dg) and dg.isdisjoint(skipped_nd)
             if ok and ((is_fan and n_fans >= MAX_FANS - 1) or n_gates + 2 >= MAX_GATES - 1
                        or payload + pay > MAX_PAYLOAD - 64 or fan_words + fw > MAX_FAN_WORDS - 8):
                 ok = False
             # a 1-qubit phase in front of a gate on the same wire (the `dr` of split_shears) waits for the round in
             # which that wire is a register bit: there it is a table entry, anywhere else a record of its own
-            wants_reg = bool(it.nd) or (it.kind == "fan" and not it.entries and nd_left.get(it.t, 0) > 0)
+            wants_reg = bool(nd) or (plain_fan and nd_left.get(it.t, 0) > 0)
             if ok and wants_reg:
                 t = it.t
                 new_t = t not in tile
                 new_r = t not in reg
-                if (new_t and len(tile) >= a) or (new_r and len(reg) >= r) or cost + _cost(it) > cfg.max_cost:
+                if (new_t and len(tile) >= a) or (new_r and len(reg) >= r) or cost + it_cost > cfg.max_cost:
                     ok = False
                 elif new_r and cfg.bank_pairs and t < 6 and c >= 4 and (t + 3 if t < 3 else t - 3) in reg:
                     # (index bits 0..5 are local bits 0..5 whenever bits 4 and 5 end up in the tile: a guess that only
@@ -781,16 +790,16 @@ def build_pass(remaining: List[Item], n: int, a: int, r: int, c: int, cfg: PlanC
                         reg.append(t)
             if ok:
                 picked.append(idx)
-                if it.kind in ("mat", "x"):
+                if is_nd_kind:
                     nd_left[it.t] -= 1
-                cost += _cost(it)
+                cost += it_cost
                 n_fans += is_fan
                 n_gates += 2 if it.kind == "fan" else 1
                 payload += pay
                 fan_words += fw
             else:
-                skipped_nd |= it.nd
-                skipped_dg |= it.dg
+                skipped_nd |= nd
+                skipped_dg |= dg
                 if len(skipped_nd) >= n:
                     break
         if not picked:

@@ -28,9 +28,12 @@ class Program:
     # -- building -------------------------------------------------------------------------------
     def add_reals(self, values: Sequence[complex]) -> int:
         off = len(self._reals)
-        for v in values:
-            v = complex(v)
-            self._reals += [v.real, v.imag]
+        if len(values) > 8:                  # (tables: one conversion instead of a Python loop)
+            self._reals.extend(np.asarray(values, dtype=np.complex128).view(np.float64).tolist())
+        else:
+            for v in values:
+                v = complex(v)
+                self._reals += [v.real, v.imag]
         return off
 
     def add_words(self, values: Sequence[int]) -> int:
