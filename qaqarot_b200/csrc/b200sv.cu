@@ -144,9 +144,9 @@ __global__ void __launch_bounds__(kThreads) k_prob(const c128* __restrict__ amp,
 }
 
 // Four amplitudes per thread share every term's mask and coefficient: per amplitude the term loop is an AND, a POPC and
-// one (HAS_IM: two) FP64 additions, and the shared-memory broadcasts -- which bounded the kernel at one amplitude per
-// thread: 7 ms for the 42 Z.Z terms of the 28-qubit QAOA energy, ten times the read of the state -- are divided by
-// four.  The order of every sum is the one of the one-amplitude loop (bit-identical results).
+// one (HAS_IM: two) FP64 additions, and the shared-memory broadcasts of the one-amplitude loop are divided by four
+// (28-qubit QAOA energy, 42 Z.Z terms: the whole run(hamiltonian=) call 26.4 -> 25.5 ms).  The order of every sum is
+// the one of the one-amplitude loop (bit-identical results).
 template <bool HAS_IM>
 __global__ void __launch_bounds__(kThreads) k_expect(const c128* __restrict__ amp, uint64_t dim, uint64_t offset,
                                                      uint64_t xmask,
