@@ -196,6 +196,77 @@ __global__ void __launch_bounds__(kThreads) k_expect(const c128* __restrict__ am
   if (threadIdx.x == 0) { partial[blockIdx.x] = accr; partial[kMaxPartials + blockIdx.x] = acci; }
 }
 
+// The same sum with TABLES instead of a loop over the terms (up to 56 terms per launch, states of at least 2^11
+// amplitudes).  The sign of term k at index i is the parity of i & zy_k = parity(lo & zy_k) xor parity(hi & zy_k) with
+// lo = i mod 2^11.  L[lo] holds the nt parities of lo as one bit mask (built once per block), H the parities of the
+// chunk's high bits (once per chunk of 2^11 amplitudes), so X = H ^ L[lo] has bit k set where term k counts negative;
+// and sum_k +-c_k is read off seven terms at a time from T[g][7-bit pattern].  Per amplitude: one 64-bit and up to
+// eight 8-byte shared-memory reads and as many additions, against nine integer instructions and an addition PER TERM
+// in k_expect -- whose 42-term QAOA energy at 28 qubits was bound by the integer pipe at ~4 ms, six reads of the state.
+constexpr int kExpLoBits = 11, kExpGroupBits = 7, kExpMaxTerms = 56, kExpGroups = kExpMaxTerms / kExpGroupBits;
+
+template <bool HAS_IM>
+__global__ void __launch_bounds__(kThreads) k_expect_tab(const c128* __restrict__ amp, uint64_t dim, uint64_t offset,
+                                                         uint64_t xmask, int nt, const uint64_t* __restrict__ zy,
+                                                         const double* __restrict__ cre, const double* __restrict__ cim,
+                                                         double* __restrict__ partial) {
+  __shared__ uint64_t L[1 << kExpLoBits];
+  __shared__ double Tr[kExpGroups][1 << kExpGroupBits];
+  __shared__ double Ti[HAS_IM ? kExpGroups : 1][1 << kExpGroupBits];
+  __shared__ uint64_t s_zy[kExpMaxTerms];
+  __shared__ double s_re[kExpMaxTerms], s_im[kExpMaxTerms];
+  for (int k = threadIdx.x; k < kExpMaxTerms; k += blockDim.x) {
+    s_zy[k] = k < nt ? zy[k] : 0ull;
+    s_re[k] = k < nt ? cre[k] : 0.0;
+    s_im[k] = k < nt ? cim[k] : 0.0;
+  }
+  __syncthreads();
+  for (uint32_t lo = threadIdx.x; lo < (1u << kExpLoBits); lo += blockDim.x) {
+    uint64_t x = 0;
+    for (int k = 0; k < nt; ++k) x |= (uint64_t)(__popcll((uint64_t)lo & s_zy[k]) & 1) << k;
+    L[lo] = x;
+  }
+  for (uint32_t e = threadIdx.x; e < (uint32_t)(kExpGroups << kExpGroupBits); e += blockDim.x) {
+    const uint32_t g = e >> kExpGroupBits, pat = e & ((1u << kExpGroupBits) - 1u);
+    double tr = 0.0, ti = 0.0;
+    for (int j = 0; j < kExpGroupBits; ++j) {
+      const int k = (int)g * kExpGroupBits + j;
+      const bool neg = (pat >> j) & 1u;
+      tr += neg ? -s_re[k] : s_re[k];
+      ti += neg ? -s_im[k] : s_im[k];
+    }
+    Tr[g][pat] = tr;
+    if (HAS_IM) Ti[g][pat] = ti;
+  }
+  __syncthreads();
+  const int ng = (nt + kExpGroupBits - 1) / kExpGroupBits;
+  const uint64_t lo_mask = (1ull << kExpLoBits) - 1ull;
+  double accr = 0.0, acci = 0.0;
+  const uint64_t n_chunks = dim >> kExpLoBits;
+  for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    const uint64_t base = c << kExpLoBits, hi = (base | offset) & ~lo_mask;
+    uint64_t H = 0;
+    for (int k = 0; k < nt; ++k) H |= (uint64_t)(__popcll(hi & s_zy[k]) & 1) << k;
+    for (uint32_t lo = threadIdx.x; lo < (1u << kExpLoBits); lo += blockDim.x) {
+      const uint64_t i = base | lo;
+      const c128 a = amp[i];
+      const c128 b = xmask ? amp[i ^ xmask] : a;
+      const uint64_t X = H ^ L[lo];
+      double wr = 0.0, wi = 0.0;
+      for (int g = 0; g < ng; ++g) {
+        const uint32_t pat = (uint32_t)(X >> (g * kExpGroupBits)) & ((1u << kExpGroupBits) - 1u);
+        wr += Tr[g][pat];
+        if (HAS_IM) wi += Ti[g][pat];
+      }
+      const double pr = b.x * a.x + b.y * a.y, pi = b.x * a.y - b.y * a.x;   // conj(b) * a
+      accr += pr * wr - pi * wi;
+      acci += pr * wi + pi * wr;
+    }
+  }
+  block_sum2(accr, acci);
+  if (threadIdx.x == 0) { partial[blockIdx.x] = accr; partial[kMaxPartials + blockIdx.x] = acci; }
+}
+
 // out[0] = sum partial[0..n), out[1] = sum partial[kMaxPartials .. +n) in a fixed order.
 __global__ void __launch_bounds__(kThreads) k_finish(const double* __restrict__ partial, int n, int two,
                                                      double* __restrict__ out) {
@@ -742,7 +813,8 @@ int b200_expect_group(b200_state* st, uint64_t xmask, int n_terms, const uint64_
   B200_REQUIRE((xmask & ~(st->dim - 1)) == 0, "b200_expect_group: xmask out of range");
   B200_CUDA(cudaSetDevice(st->device));
   *out_re = *out_im = 0.0;
-  const int kChunk = 1024;
+  const bool tables = st->n >= kExpLoBits && getenv("B200_EXPECT_LOOP") == nullptr;
+  const int kChunk = tables ? kExpMaxTerms : 1024;
   for (int base = 0; base < n_terms; base += kChunk) {
     const int nt = std::min(kChunk, n_terms - base);
     if (ensure_capacity(st, nt, 2 * (size_t)nt)) return 1;
@@ -754,7 +826,13 @@ int b200_expect_group(b200_state* st, uint64_t xmask, int n_terms, const uint64_
     const size_t smem = (size_t)nt * (sizeof(uint64_t) + 2 * sizeof(double));
     bool has_im = false;
     for (int k = 0; k < nt; ++k) has_im |= cim[base + k] != 0.0;
-    if (has_im)
+    if (tables && has_im)
+      k_expect_tab<true><<<blocks, kThreads, 0, st->stream>>>(st->amp, st->dim, st->index_offset, xmask, nt, st->d_words,
+                                                             st->d_reals, st->d_reals + nt, st->d_partial);
+    else if (tables)
+      k_expect_tab<false><<<blocks, kThreads, 0, st->stream>>>(st->amp, st->dim, st->index_offset, xmask, nt, st->d_words,
+                                                              st->d_reals, st->d_reals + nt, st->d_partial);
+    else if (has_im)
       k_expect<true><<<blocks, kThreads, smem, st->stream>>>(st->amp, st->dim, st->index_offset, xmask, nt, st->d_words,
                                                             st->d_reals, st->d_reals + nt, st->d_partial);
     else
