@@ -495,3 +495,36 @@ def test_c2_qft_30_qubits_against_the_analytic_answer():
             assert maxabs(got, want) <= 1e-14        # |amp| = 2^-15, so this is 3e-10 relative
     finally:
         be.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [10, 14])
+def test_expect_group_with_shard_offset_many_terms_and_complex_coefficients(n):
+    """b200_expect_group as a shard of a larger register sees it (index offset above n), with more terms than one table
+    launch holds (k_expect_tab: 56) and complex coefficients; below 2^11 amplitudes the loop kernel.  Against the
+    definition, sum conj(a[i ^ x]) a[i] sum_k c_k (-1)^popc((i | offset) & zy_k), in numpy."""
+    from qaqarot_b200.device import DeviceState
+    rng = np.random.default_rng(4 + n)
+    dim = 1 << n
+    psi = rng.standard_normal(dim) + 1j * rng.standard_normal(dim)
+    psi /= np.linalg.norm(psi)
+    st = DeviceState(n)
+    st.upload(psi)
+    idx = np.arange(dim, dtype=np.uint64)
+    for offset_bits, n_terms, cplx, xmask in ((0, 7, False, 0), (3, 60, False, 0), (2, 130, True, 0b1011 << 3), (1, 56, True, 5)):
+        offset = offset_bits << n
+        st.set_index_offset(offset)
+        zy = [int(v) for v in rng.integers(0, 1 << (n + 2), n_terms)]
+        c = rng.standard_normal(n_terms) + (1j * rng.standard_normal(n_terms) if cplx else 0)
+        w = np.zeros(dim, dtype=complex)
+        for m, ck in zip(zy, c):
+            v = (idx | np.uint64(offset)) & np.uint64(m)
+            par = np.zeros(dim, dtype=np.uint64)
+            for b in range(n + 2):
+                par ^= (v >> np.uint64(b)) & np.uint64(1)
+            w += np.where(par == 1, -ck, ck)
+        b = psi[(idx ^ np.uint64(xmask)).astype(np.int64)]
+        want = complex(np.sum(np.conj(b) * psi * w))
+        got = st.expect_group(xmask, zy, list(c))
+        assert abs(got - want) <= 1e-12 * max(1.0, abs(want)), (offset_bits, n_terms, got, want)
+    st.close()
