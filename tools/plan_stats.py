@@ -39,11 +39,13 @@ def main():
             times = json.load(f)["ms"][-1]
     hbm_ms = 32.0 * 2 ** n / 6554.9e9 * 1e3
     tot = dict(fp64=0.0, ms=0.0)
+    all_stats = []
     k = 0
     for i, o in enumerate(prog._ops):
         if o[0] != 16:
             continue
         st = pass_stats(prog._words, o[5], n, prog._reals)
+        all_stats.append(st)
         fp_ms = st["fp64"] * 2 ** n / (SM * DFMA_PER_CLK * CLK) * 1e3
         ms = times[i + (len(times) - len(prog._ops))] if times else float("nan")
         tot["fp64"] += st["fp64"]
@@ -52,6 +54,11 @@ def main():
               f"tab {st['tabs']:2d} fan {st['fans']:2d} other {st['other']:2d}) fp64/amp {st['fp64']:6.1f} = {fp_ms:5.2f} ms "
               f"(hbm {hbm_ms:.2f}) runs {st['runs']} conflict-rounds {st['conflict_rounds']}  measured {ms:6.2f} ms  tile {st['tile'][3:]}")
         k += 1
+    # round-2 fit of the measured pass times at 30 qubits: 2.8 ms + 1.3 ms per round + 0.017 ms per DFMA/amp +
+    # 0.17 ms per record, scaled with the state size
+    model = sum(2.8 + 1.3 * s["rounds"] + 0.017 * s["fp64"] + 0.17 * s["records"] for s in all_stats) * 2.0 ** (n - 30)
+    print(f"cost model (round-2 fit): {model:.1f} ms for {sum(s['rounds'] for s in all_stats)} rounds, "
+          f"{sum(s['records'] for s in all_stats)} records")
     print(f"total fp64/amp {tot['fp64']:.0f} = {tot['fp64'] * 2 ** n / (SM * DFMA_PER_CLK * CLK) * 1e3:.1f} ms at 64 DFMA/clk/SM, "
           f"{k} passes = {k * hbm_ms:.1f} ms of HBM time, measured {tot['ms']:.1f} ms")
 
