@@ -363,10 +363,10 @@ def run_b200(args):
     n = args.qubits
     circ, wl = build_workload(args.workload, n, args.depth)
     cfg = None
-    if args.tile_bits or args.no_shears or args.row_bits != 4:
+    if args.tile_bits or args.no_shears or args.row_bits != 4 or args.no_bank_pairs:
         from qaqarot_b200.planner import PlanConfig
         cfg = PlanConfig(a=args.tile_bits or 12, r=args.reg_bits, c=args.row_bits, shears=not args.no_shears,
-                         **({"max_cost": args.max_cost} if args.max_cost else {}))
+                         bank_pairs=not args.no_bank_pairs, **({"max_cost": args.max_cost} if args.max_cost else {}))
     be = B200Backend(device=0, fusion=not args.no_fusion, plan_config=cfg)
     res = measure_resident(be, circ, n, args.steps, args.warmup, clock_index=0, detail=args.detail)
     comp, prog, st, sec_per_step = res["comp"], res["prog"], res["state"], res["sec_per_step"]
@@ -666,6 +666,7 @@ def main():
     ap.add_argument("--reg-bits", type=int, default=4, help="with --tile-bits: register bits per round (3 only with 11)")
     ap.add_argument("--max-cost", type=float, default=0.0, help="with --tile-bits: planner's DFMA budget per amplitude per pass")
     ap.add_argument("--row-bits", type=int, default=4, help="planner experiment: low index bits every tile must contain (2^c * 16 B rows)")
+    ap.add_argument("--no-bank-pairs", action="store_true", help="planner experiment: PlanConfig.bank_pairs = False")
     ap.add_argument("--no-shears", action="store_true", help="planner experiment: keep 1-qubit gates as general 2x2 matrices")
     ap.add_argument("--detail", default="", help="write per-op device times of the timed steps to this JSON file")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
