@@ -288,8 +288,8 @@ class B200Backend(_Base):
         try:
             model = R.ParamModel(list(gates), last_angles, plan_prefix)
             self.replay_stats["built"] += 1
-        except R.NotModelable:
-            model = None
+        except Exception:                                    # NotModelable, or a probe the planner itself rejects: the
+            model = None                                     # loop simply goes on without a model for this structure
             self.replay_stats["unmodelable"] += 1
         if len(self._models) > 16:
             self._models.clear()
