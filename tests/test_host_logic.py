@@ -290,3 +290,39 @@ def test_objective_loop_with_blueqats_own_qaoa_ansatz():
             want = circ.run(backend="numpy")
         assert maxabs(circ.run(backend=be), want) <= 1e-12
     assert be.replay_stats["built"] == 1 and be.replay_stats["hits"] == 3 and be.replay_stats["misses"] == 0
+
+
+def test_param_model_declines_what_it_cannot_describe():
+    """ParamModel.evaluate returns None -- the backend then plans first, as always -- when gates that shared an angle no
+    longer do, or when a rotation leaves the range in which its slot is affine in the gate angle (rx(beta) beyond pi: the
+    planner's angle turns around there); structure_key ignores angle values and nothing else."""
+    import dataclasses
+    from qaqarot_b200 import param_replay as R, planner as P, workloads as W
+    from qaqarot_b200.lowering import lower
+    n = 12
+    cfg = dataclasses.replace(P.DEFAULT, exact_rotations=True)
+
+    def plan_prefix(gates):
+        low = lower(tuple(gates), n, 0)
+        return P.plan(low.prims, n, cfg, free_initial_layout=True)
+    c1, c2 = W.qaoa_maxcut(n, p=2, seed=1)[0], W.qaoa_maxcut(n, p=2, seed=2)[0]
+    assert R.structure_key(c1.ops, n) == R.structure_key(c2.ops, n)
+    assert R.structure_key(c1.ops, n) != R.structure_key(W.qaoa_maxcut(n, p=3, seed=1)[0].ops, n)
+    model = R.ParamModel(list(c2.ops), R.angle_values(c1.ops), plan_prefix)
+    assert len(model.members) == 4                                       # 2 betas, 2 gammas
+    v = R.angle_values(c2.ops)
+    assert np.abs(model.evaluate(v) - np.asarray(plan_prefix(c2.ops)._reals)).max() <= 1e-13
+    w = v.copy()
+    w[model.members[0][0]] += 0.1                                        # one gate of a group goes its own way
+    assert model.evaluate(w) is None
+    for g, ix in enumerate(model.members):                               # an rx angle beyond pi
+        w = v.copy()
+        w[ix] = 3.5
+        got = model.evaluate(w)
+        if got is None:
+            break
+    else:
+        raise AssertionError("no group is a rotation angle")
+    # the rebuilt gates are new objects with the new angles, the others are shared
+    gates = R.with_angles(c2.ops, v + 0.25)
+    assert np.allclose(R.angle_values(gates), v + 0.25) and gates[0] is c2.ops[0]
