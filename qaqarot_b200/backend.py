@@ -26,6 +26,7 @@ import numpy as np
 
 from .lowering import Lowered, Prim, lower
 from .pauli import canonical_terms
+from . import param_replay as R
 from .program import Program, unfused_program
 
 try:                                                   # subclass blueqat's base class when it is importable
@@ -265,7 +266,6 @@ class B200Backend(_Base):
     def _replay_model(self, gates, n_qubits: int):
         """The ParamModel of this gate structure, built when the structure shows up for the third time in a row with
         other angles; None when there is none (yet) or the structure is not modelable."""
-        from . import param_replay as R
         key = R.structure_key(gates, n_qubits)
         angles = R.angle_values(gates)
         last_key, last_angles = self._last_key, self._last_angles
@@ -340,7 +340,7 @@ class B200Backend(_Base):
         if spec is not None:
             real = comp.prefix
             if (model.matches(real) and len(real._reals) == spec.size
-                    and float(np.abs(np.asarray(real._reals) - spec).max()) <= 1e-12):
+                    and float(np.abs(np.asarray(real._reals) - spec).max()) <= R.TOL):
                 self.replay_stats["hits"] += 1
             else:
                 # a branch of the planner went the other way for these angles: run the real plan, forget the model
