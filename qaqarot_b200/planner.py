@@ -749,19 +749,18 @@ def build_pass(remaining: List[Item], n: int, a: int, r: int, c: int, cfg: PlanC
         info.append((kind not in ("swap", "perm", "exchange"), int(_payload(it, a, r) * pay_scale), is_fan,
                      3 + len(it.entries) if is_fan else (1 if kind in ("phase", "fan") else 0), _cost(it),
                      kind in ("mat", "x"), kind == "fan" and not it.entries))
+    nd_left: Dict[int, int] = {}                   # wire -> non-diagonal gates on it still to be scheduled
+    for idx in range(limit):
+        if info[idx][5]:
+            t = remaining[idx].t
+            nd_left[t] = nd_left.get(t, 0) + 1
+    alive = list(range(limit))                     # the items not yet placed, in program order
     for _ in range(cfg.max_rounds):
         reg: List[int] = []
         picked: List[int] = []
         skipped_nd: set = set()
         skipped_dg: set = set()
-        nd_left: Dict[int, int] = {}               # wire -> non-diagonal gates on it still to be scheduled
-        for idx in range(limit):
-            if not done[idx] and info[idx][5]:
-                t = remaining[idx].t
-                nd_left[t] = nd_left.get(t, 0) + 1
-        for idx in range(limit):
-            if done[idx]:
-                continue
+        for idx in alive:
             it = remaining[idx]
             sched, pay, is_fan, fw, it_cost, is_nd_kind, plain_fan = info[idx]
             nd, dg = it.nd, it.dg
@@ -811,6 +810,7 @@ def build_pass(remaining: List[Item], n: int, a: int, r: int, c: int, cfg: PlanC
             rounds.append(Round(reg, [remaining[i] for i in picked]))
         for i in picked:
             done[i] = True
+        alive = [i for i in alive if not done[i]]
     # complete the tile with the lowest unused bits, then every round's register set with unused tile bits
     q = c
     while len(tile) < a:
@@ -950,10 +950,13 @@ class _Group:
             assert self.diag is None
             m = len(self.sel_bits)
             # [variant][rho], variants TAB_PITCH entries apart (csrc/tile.cu: compile-time offsets, no bank conflicts)
-            tabs = np.ones((1 << m, TAB_PITCH if m else 1 << self.r), dtype=complex)
+            size = 1 << self.r
+            base = self.tab.tolist()
+            pad = [1.0 + 0j] * ((TAB_PITCH if m else size) - size)
+            tabs: List[complex] = []
             for var in range(1 << m):
                 on = {q for i, q in enumerate(self.sel_bits) if (var >> i) & 1}
-                t = self.tab.copy()
+                t = list(base)
                 for kt, tsel, w0, entries in self.sel_fans:
                     if tsel is not None and tsel not in on:
                         continue
@@ -961,11 +964,14 @@ class _Group:
                     for q, w in entries.items():
                         if q in on:
                             f *= w
-                    for rho in range(1 << self.r):
-                        if kt is None or (rho >> kt) & 1:
-                            t[rho] *= f
-                tabs[var, :1 << self.r] = t
-            tabs = list(tabs.reshape(-1))
+                    if kt is None:
+                        t = [x * f for x in t]
+                    else:
+                        for rho in range(size):
+                            if (rho >> kt) & 1:
+                                t[rho] *= f
+                tabs += t
+                tabs += pad
             kw.update(dk=D_TAB, roff_d=prog.add_reals(tabs), fid=p[2])
             kw.setdefault("rm", sel)
         elif self.diag is not None:
