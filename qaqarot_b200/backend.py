@@ -270,15 +270,23 @@ class B200Backend(_Base):
         angles = R.angle_values(gates)
         last_key, last_angles = self._last_key, self._last_angles
         self._last_key, self._last_angles = key, angles
+        generation = 0
         if key in self._models:
-            return self._models[key], angles
-        if key != last_key or angles.size == 0 or np.array_equal(angles, last_angles):
+            model = self._models[key]
+            # a model describes the planner around the angles it was built at (every rotation within a quarter turn of
+            # there): a loop that has walked out of that range, and stays out, gets a new one around where it is now
+            if (model is None or model.declined < R.RECENTRE_AFTER or model.generation >= R.MAX_RECENTRES
+                    or key != last_key or np.array_equal(angles, last_angles)):
+                return model, angles
+            generation = model.generation + 1
+        elif key != last_key or angles.size == 0 or np.array_equal(angles, last_angles):
             self._repeats = 0
             return None, angles
-        # the model costs one plan per distinct angle: only a loop pays that back, so wait for the third call in a row
-        self._repeats += 1
-        if self._repeats < 2:
-            return None, angles
+        else:
+            # the model costs one plan per distinct angle: only a loop pays that back, so wait for the third call in a row
+            self._repeats += 1
+            if self._repeats < 2:
+                return None, angles
         planner = self._planner_exact
 
         def plan_prefix(g):
@@ -287,6 +295,7 @@ class B200Backend(_Base):
             return planner(low.prims[:k], n_qubits, free_initial_layout=True)
         try:
             model = R.ParamModel(list(gates), last_angles, plan_prefix)
+            model.generation = generation
             self.replay_stats["built"] += 1
         except Exception:                                    # NotModelable, or a probe the planner itself rejects: the
             model = None                                     # loop simply goes on without a model for this structure
@@ -331,6 +340,7 @@ class B200Backend(_Base):
             if model is not None:
                 planner = self._planner_exact            # (the model describes plans with exact rotations)
                 spec = model.evaluate(angles)
+                model.declined = 0 if spec is not None else model.declined + 1
                 if spec is not None:
                     # launch with the predicted payload now; the real plan is made while the device runs
                     prog = model.program(spec)

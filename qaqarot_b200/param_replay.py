@@ -19,6 +19,10 @@ circuit for real while the device is already running (the plan costs about as mu
 device time), and compares.  Equal (<= TOL = 1e-13): the result stands and the iteration cost the device time plus ~1 ms.
 Different (a branch of the planner went the other way for these angles): the circuit runs again with the real plan and
 the model is dropped.  The answer never depends on the model being right.
+
+The model holds around the angles it was built at (every merged rotation within |t| <= pi/2; beyond, the planner turns
+the rotation around and the slot is no longer affine): ``evaluate`` returns None outside, the backend plans first as it
+always did, and after RECENTRE_AFTER such calls in a row it builds a new model around the angles the loop has reached.
 """
 from __future__ import annotations
 
@@ -32,6 +36,8 @@ from .program import Program
 
 DELTA = 1.0e-3            # probe step: exponents up to ~3000 / (group) stay below a phase wrap
 MAX_GROUPS = 32           # one probe plan per group
+RECENTRE_AFTER = 3        # calls in a row the model had to decline before the backend builds a new one around the current angles
+MAX_RECENTRES = 4         # ... at most so many times per gate structure (a loop that keeps jumping gets no model)
 TOL = 1.0e-13             # predicted against planned payload: 1.3e-14 at most over QAOA-28 p=4 angle sweeps (the planner's
                           # own products of exp() round as much), so an order of magnitude of head-room; a payload entry off
                           # by TOL moves an amplitude by at most TOL per record, well inside the 1e-12 parity bar
@@ -125,6 +131,8 @@ class ParamModel:
             groups.setdefault((float(a), float(b)), []).append(i)
         if len(groups) > MAX_GROUPS:
             raise NotModelable(f"{len(groups)} independent angles")
+        self.declined = 0          # consecutive calls evaluate() returned None for (kept by the backend)
+        self.generation = 0        # how many models of this structure came before this one
         self.members = [np.array(ix, dtype=np.int64) for ix in groups.values()]
         self.n_values = vals.size
         self.u0 = np.array([vals[ix[0]] for ix in self.members])

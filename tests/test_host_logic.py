@@ -262,6 +262,35 @@ def test_objective_loop_launches_from_the_planner_model_and_checks_it():
     assert be2.replay_stats["hits"] == 0
 
 
+def test_objective_loop_that_walks_out_of_the_models_range_gets_a_new_model():
+    """A ParamModel holds within a quarter turn of the rotations it was built at.  An optimiser that moves an rx angle past
+    pi leaves that range: the model declines (the backend plans first, as always), and after three such calls in a row a
+    new model is built around the angles the loop has reached.  Every statevector against the oracle."""
+    from qaqarot_b200 import Circuit, param_replay as R, workloads as W
+    from helpers import cpu_backend
+    from oracle import sv_oracle as O
+    n = 12
+    edges = W.ring_edges(n)
+
+    def ansatz(beta, gamma):
+        c = Circuit(n).h[:]
+        for i, j in edges:
+            c.cx[i, j].rz(-2.0 * gamma)[j].cx[i, j]
+        return c.rx(beta)[:]
+    be = cpu_backend(True)
+    stats = []
+    for k, (beta, gamma) in enumerate([(0.5, 0.3), (0.6, 0.35), (0.7, 0.4), (0.8, 0.45),         # built on the third, hit
+                                       (3.5, 0.5), (3.6, 0.55), (3.7, 0.6),                     # out of range: declined
+                                       (3.8, 0.65), (3.9, 0.7)]):                               # re-centred, hit
+        c = ansatz(beta, gamma)
+        assert maxabs(c.run(backend=be), O.OracleBackend().run(c.ops, n)) <= 1e-12, k
+        stats.append((be.replay_stats["built"], be.replay_stats["hits"]))
+    assert be.replay_stats["misses"] == 0 and be.replay_stats["unmodelable"] == 0
+    assert stats == [(0, 0), (0, 0), (1, 1), (1, 2), (1, 2), (1, 2), (1, 2), (2, 3), (2, 4)], stats
+    (model,) = [m for m in be._models.values() if m is not None]
+    assert model.generation == 1 and model.declined == 0
+
+
 @pytest.mark.reference
 def test_objective_loop_with_blueqats_own_qaoa_ansatz():
     """The reference's own call path (vqe.py:130-144 QaoaAnsatz.get_circuit, rebuilt for every angle vector): genuine
